@@ -158,7 +158,14 @@ typedef struct rt1w_camera {
     double time0, time1;
 } rt1w_camera;
 
-#define RT1W_FLAG_STATS 1u /* also accumulate per-pixel clamped sum and sum of squares (test statistic) */
+#define RT1W_FLAG_STATS 1u   /* also accumulate per-pixel clamped sum and sum of squares (test statistic) */
+#define RT1W_FLAG_PROFILE 2u /* bracket every kernel launch with CUDA events and fill rt1w_render_stats.kernel_ms (slower) */
+
+/* kernel slots of rt1w_render_stats.kernel_ms / kernel_launches */
+#define RT1W_KERNEL_GENERATE 0
+#define RT1W_KERNEL_EXTEND 1
+#define RT1W_KERNEL_SHADE0 2 /* + rt1w_material_type (LAMBERTIAN .. ISOTROPIC, DIFFUSE_LIGHT) */
+#define RT1W_KERNEL_COUNT 7
 
 typedef struct rt1w_render_params {
     int32_t width;          /* image_width  (main.rs:799) */
@@ -180,8 +187,8 @@ typedef struct rt1w_render_stats {
     uint64_t waves;       /* wavefront iterations */
     uint64_t launches;    /* kernels launched inside the render */
     double render_ms;     /* device time generate -> accumulate, CUDA events on the render stream */
-    double extend_ms;     /* device time of the extend kernel summed over waves (0 unless profiling flag) */
-    uint64_t nan_samples; /* reserved */
+    double kernel_ms[RT1W_KERNEL_COUNT];         /* per kernel: device time summed over its launches (RT1W_FLAG_PROFILE only) */
+    uint64_t kernel_launches[RT1W_KERNEL_COUNT]; /* per kernel: launches timed (RT1W_FLAG_PROFILE only) */
 } rt1w_render_stats;
 
 typedef struct rt1w_scene_info {

@@ -85,6 +85,18 @@ struct AABB {
         return true;
     }
 };
+// closed-interval variant used only by the tie sweep of oracle_trace_closest (not in the reference)
+inline bool aabb_hit_closed(const AABB &b, const Ray &ray, Float t_min, Float t_max) {
+    for (int a = 0; a < 3; ++a) {
+        Float inv_d = 1.0 / ray.direction[a];
+        Float t0 = (b.minimum[a] - ray.origin[a]) * inv_d, t1 = (b.maximum[a] - ray.origin[a]) * inv_d;
+        if (inv_d < 0.0) std::swap(t0, t1);
+        if (t0 > t_min) t_min = t0;
+        if (t1 < t_max) t_max = t1;
+        if (t_max < t_min) return false;
+    }
+    return true;
+}
 static AABB surrounding_box(AABB a, AABB b) { // aabb.rs:35-52
     return AABB{v3(std::fmin(a.minimum.x, b.minimum.x), std::fmin(a.minimum.y, b.minimum.y), std::fmin(a.minimum.z, b.minimum.z)),
                 v3(std::fmax(a.maximum.x, b.maximum.x), std::fmax(a.maximum.y, b.maximum.y), std::fmax(a.maximum.z, b.maximum.z))};
@@ -238,6 +250,23 @@ using Hit = std::optional<HitRecord>;
 struct TraceReplay {
     bool active = false;
     uint64_t seed = 0, ray_index = 0;
+    // tie bookkeeping (parity only): every leaf hit that was accepted at some point of the walk, and
+    // whether a leaf rejected a candidate that lies within 1e-9 relative of the range end
+    int n_cand = 0;
+    int cand_prim[32];
+    double cand_t[32];
+    bool near_reject = false;
+    void reset() { n_cand = 0, near_reject = false; }
+    void accept(int prim, double t) {
+        if (!active || prim < 0) return;
+        if (n_cand < 32) cand_prim[n_cand] = prim, cand_t[n_cand] = t, ++n_cand;
+        else near_reject = true;
+    }
+    void reject(int prim, double t, double t_min, double t_max) {
+        if (!active || prim < 0) return;
+        const double tol = 1e-9;
+        if ((t > t_max && t <= t_max + tol * std::fmax(1.0, std::fabs(t_max))) || (t < t_min && t >= t_min - tol)) near_reject = true;
+    }
 };
 static thread_local TraceReplay g_replay;
 
@@ -380,9 +409,14 @@ struct Sphere : Hittable {
         Float sqrtd = std::sqrt(discriminant);
         Float root = (-half_b - sqrtd) / a;
         if (root < t_min || t_max < root) {
+            g_replay.reject(prim, root, t_min, t_max);
             root = (-half_b + sqrtd) / a;
-            if (root < t_min || t_max < root) return std::nullopt;
+            if (root < t_min || t_max < root) {
+                g_replay.reject(prim, root, t_min, t_max);
+                return std::nullopt;
+            }
         }
+        g_replay.accept(prim, root);
         V3 position = ray.at(root);
         V3 outward_normal = (position - center) / radius;
         Float u, v;
@@ -423,9 +457,14 @@ struct MovingSphere : Hittable {
         Float sqrtd = std::sqrt(discriminant);
         Float root = (-half_b - sqrtd) / a;
         if (root < t_min || t_max < root) {
+            g_replay.reject(prim, root, t_min, t_max);
             root = (-half_b + sqrtd) / a;
-            if (root < t_min || t_max < root) return std::nullopt;
+            if (root < t_min || t_max < root) {
+                g_replay.reject(prim, root, t_min, t_max);
+                return std::nullopt;
+            }
         }
+        g_replay.accept(prim, root);
         V3 position = ray.at(root);
         V3 outward_normal = (position - center(ray.time)) / radius;
         Float u, v;
@@ -449,10 +488,17 @@ template <int AXIS> struct AARect : Hittable {
     int prim = -1;
     Hit hit(const Ray &ray, Float t_min, Float t_max, MyRng &) const override { // aarect.rs:46-72, 84-110, 152-178
         Float t = (k - ray.origin[AXIS]) / ray.direction[AXIS];
-        if (t < t_min || t > t_max) return std::nullopt;
+        if (t < t_min || t > t_max) {
+            if (g_replay.active) {
+                Float ra = ray.origin[A] + t * ray.direction[A], rb = ray.origin[B] + t * ray.direction[B];
+                if (!(ra < a0 || ra > a1 || rb < b0 || rb > b1)) g_replay.reject(prim, t, t_min, t_max);
+            }
+            return std::nullopt;
+        }
         Float a = ray.origin[A] + t * ray.direction[A];
         Float b = ray.origin[B] + t * ray.direction[B];
         if (a < a0 || a > a1 || b < b0 || b > b1) return std::nullopt;
+        g_replay.accept(prim, t);
         Float u = (a - a0) / (a1 - a0), v = (b - b0) / (b1 - b0);
         V3 outward_normal = v3(AXIS == 0 ? 1.0 : 0.0, AXIS == 1 ? 1.0 : 0.0, AXIS == 2 ? 1.0 : 0.0);
         return HitRecord::make(ray.at(t), outward_normal, t, u, v, ray, material, prim);
@@ -523,6 +569,13 @@ struct BVHNode : Hittable {
             node->left = std::move(l), node->right = std::move(r);
         }
         return node;
+    }
+    void release_leaves(std::vector<HittableBox> &out) { // parity bookkeeping: dismantles the tree
+        for (HittableBox *c : {&left, &right}) {
+            if (!*c) continue;
+            if (auto *b = dynamic_cast<BVHNode *>(c->get())) b->release_leaves(out);
+            else out.push_back(std::move(*c));
+        }
     }
     void shape(int depth, int &n_nodes, int &max_depth) const {
         ++n_nodes;
@@ -689,6 +742,7 @@ struct ConstantMedium : Hittable {
         Float hit_distance = neg_inv_density * std::log(xi);
         if (hit_distance > distance_inside_boundary) return std::nullopt;
         Float t = rec1->t + hit_distance / ray_length;
+        g_replay.accept(prim, t);
         HitRecord rec{ray.at(t), v3(1.0, 0.0, 0.0), t, 0.0, 0.0, true, phase_function, prim};
         return rec;
     }
@@ -759,6 +813,9 @@ struct Scene {
     HittableList lights;
     bool has_lights = false;
     int n_prims = 0;
+    // parity bookkeeping only: every numbered leaf once more, standing alone under a copy of its
+    // wrapper chain, so that ties can be found independently of any BVH order
+    std::vector<HittableBox> flat;
 };
 
 struct Loader {
@@ -767,6 +824,27 @@ struct Loader {
     MyRng rng;
     int next_prim = 0;
     bool number_prims = true;
+    std::vector<int> wrappers; // node ids of the Translate / RotateY / FlipFace wrappers above the current node
+
+    void add_flat(int prim, HittableBox leaf) {
+        if (prim < 0) return;
+        for (size_t i = wrappers.size(); i-- > 0;) {
+            const rt1w_node &w = d.nodes[wrappers[i]];
+            if (w.type == RT1W_NODE_TRANSLATE) {
+                auto t = std::make_unique<Translate>();
+                t->hittable = std::move(leaf), t->offset = v3(w.p[0], w.p[1], w.p[2]);
+                leaf = std::move(t);
+            } else if (w.type == RT1W_NODE_ROTATE_Y) {
+                leaf = RotateY::make(std::move(leaf), w.p[1], w.p[2], w.p[0]);
+            } else {
+                auto f = std::make_unique<FlipFace>();
+                f->inner = std::move(leaf);
+                leaf = std::move(f);
+            }
+        }
+        if (scene.flat.size() <= size_t(prim)) scene.flat.resize(size_t(prim) + 1);
+        scene.flat[size_t(prim)] = std::move(leaf);
+    }
 
     std::shared_ptr<Texture> texture(int id) {
         if (id < 0 || id >= d.n_textures) throw std::runtime_error("texture id out of range");
@@ -847,31 +925,55 @@ struct Loader {
         case RT1W_NODE_SPHERE: {
             auto s = std::make_unique<Sphere>();
             s->center = v3(p[0], p[1], p[2]), s->radius = p[3], s->material = material(n.material), s->prim = take_prims(1);
+            add_flat(s->prim, std::make_unique<Sphere>(*s));
             return s;
         }
         case RT1W_NODE_MOVING_SPHERE: {
             auto s = std::make_unique<MovingSphere>();
             s->center0 = v3(p[0], p[1], p[2]), s->center1 = v3(p[3], p[4], p[5]), s->time0 = p[6], s->time1 = p[7], s->radius = p[8];
             s->material = material(n.material), s->prim = take_prims(1);
+            add_flat(s->prim, std::make_unique<MovingSphere>(*s));
             return s;
         }
-        case RT1W_NODE_XY_RECT: { auto r = std::make_unique<XYRect>(); r->a0 = p[0], r->a1 = p[1], r->b0 = p[2], r->b1 = p[3], r->k = p[4], r->material = material(n.material), r->prim = take_prims(1); return r; }
-        case RT1W_NODE_XZ_RECT: { auto r = std::make_unique<XZRect>(); r->a0 = p[0], r->a1 = p[1], r->b0 = p[2], r->b1 = p[3], r->k = p[4], r->material = material(n.material), r->prim = take_prims(1); return r; }
-        case RT1W_NODE_YZ_RECT: { auto r = std::make_unique<YZRect>(); r->a0 = p[0], r->a1 = p[1], r->b0 = p[2], r->b1 = p[3], r->k = p[4], r->material = material(n.material), r->prim = take_prims(1); return r; }
+        case RT1W_NODE_XY_RECT: { auto r = std::make_unique<XYRect>(); r->a0 = p[0], r->a1 = p[1], r->b0 = p[2], r->b1 = p[3], r->k = p[4], r->material = material(n.material), r->prim = take_prims(1); add_flat(r->prim, std::make_unique<XYRect>(*r)); return r; }
+        case RT1W_NODE_XZ_RECT: { auto r = std::make_unique<XZRect>(); r->a0 = p[0], r->a1 = p[1], r->b0 = p[2], r->b1 = p[3], r->k = p[4], r->material = material(n.material), r->prim = take_prims(1); add_flat(r->prim, std::make_unique<XZRect>(*r)); return r; }
+        case RT1W_NODE_YZ_RECT: { auto r = std::make_unique<YZRect>(); r->a0 = p[0], r->a1 = p[1], r->b0 = p[2], r->b1 = p[3], r->k = p[4], r->material = material(n.material), r->prim = take_prims(1); add_flat(r->prim, std::make_unique<YZRect>(*r)); return r; }
         case RT1W_NODE_AABOX: {
             MaterialArc m = material(n.material);
             int first = take_prims(6);
+            if (first >= 0) { // the six sides again, one by one (same order as AABox::make)
+                MyRng scratch = MyRng::seed_from_u64(0);
+                auto twin = AABox::make(v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), m, scratch, first);
+                std::vector<HittableBox> sides;
+                twin->sides->release_leaves(sides);
+                for (auto &side : sides) {
+                    int id = -1;
+                    if (auto *r = dynamic_cast<XYRect *>(side.get())) id = r->prim;
+                    else if (auto *r = dynamic_cast<XZRect *>(side.get())) id = r->prim;
+                    else if (auto *r = dynamic_cast<YZRect *>(side.get())) id = r->prim;
+                    add_flat(id, std::move(side));
+                }
+            }
             return AABox::make(v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), m, rng, first);
         }
         case RT1W_NODE_TRANSLATE: {
             auto t = std::make_unique<Translate>();
+            wrappers.push_back(id);
             t->hittable = child(0), t->offset = v3(p[0], p[1], p[2]);
+            wrappers.pop_back();
             return t;
         }
-        case RT1W_NODE_ROTATE_Y: return RotateY::make(child(0), p[1], p[2], p[0]);
+        case RT1W_NODE_ROTATE_Y: {
+            wrappers.push_back(id);
+            HittableBox c = child(0);
+            wrappers.pop_back();
+            return RotateY::make(std::move(c), p[1], p[2], p[0]);
+        }
         case RT1W_NODE_FLIP_FACE: {
             auto f = std::make_unique<FlipFace>();
+            wrappers.push_back(id);
             f->inner = child(0);
+            wrappers.pop_back();
             return f;
         }
         case RT1W_NODE_CONSTANT_MEDIUM: {
@@ -883,6 +985,14 @@ struct Loader {
             number_prims = saved;
             m->phase_function = material(n.material);
             m->neg_inv_density = -1.0 / p[0];
+            if (m->prim >= 0) {
+                auto twin = std::make_unique<ConstantMedium>();
+                twin->prim = m->prim, twin->phase_function = m->phase_function, twin->neg_inv_density = m->neg_inv_density;
+                number_prims = false;
+                twin->boundary = child(0);
+                number_prims = saved;
+                add_flat(m->prim, std::move(twin));
+            }
             return m;
         }
         case RT1W_NODE_BVH: {
@@ -925,7 +1035,7 @@ oracle_scene *oracle_scene_load(const rt1w_scene_desc *desc, uint64_t bvh_seed) 
             }
             sc.perlins.push_back(p);
         }
-        Loader ld{*desc, sc, MyRng::seed_from_u64(bvh_seed)};
+        Loader ld{*desc, sc, MyRng::seed_from_u64(bvh_seed), 0, true, {}};
         sc.world = ld.node(desc->world);
         sc.n_prims = ld.next_prim;
         sc.has_lights = desc->has_lights != 0;
@@ -962,15 +1072,35 @@ int32_t oracle_trace_closest(const oracle_scene *s, const rt1w_ray *rays, size_t
     const Hittable &world = *s->scene.world;
     AABB wb = world.bounding_box(0.0, 1.0);
     const double extent = std::fmax(std::fmax(wb.maximum.x - wb.minimum.x, wb.maximum.y - wb.minimum.y), wb.maximum.z - wb.minimum.z);
-    const double rel = 2e-6;
+    // The product solves ray/primitive intersections in f64 from the same f32 inputs, so only genuine
+    // (near-)ties are excluded: two leaves within 1e-9 relative of the winning t, a candidate within
+    // 1e-9 of the range ends, or a winner that changes under a 1e-9-relative perturbation of the ray.
+    const double rel = 1e-9;
 #pragma omp parallel for schedule(dynamic, 1024)
     for (long long i = 0; i < (long long)n; ++i) {
         MyRng rng = MyRng::seed_from_u64(uint64_t(i));
         g_replay.active = true, g_replay.seed = seed, g_replay.ray_index = uint64_t(i);
         Ray r{v3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), v3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]),
               double(rays[i].time)};
+        g_replay.reset();
         Hit h = world.hit(r, 0.001, INF, rng);
         int id = h ? h->prim : -1;
+        bool tie = g_replay.near_reject;
+        if (h) {
+            const double tol = 1e-9 * std::fmax(1.0, std::fabs(h->t));
+            for (int c = 0; c < g_replay.n_cand; ++c)
+                if (g_replay.cand_prim[c] != id && std::fabs(g_replay.cand_t[c] - h->t) <= tol) tie = true;
+            // BVH-independent sweep: any other leaf whose own hit lands within tol of the winner
+            // (the reference may never reach it: an un-padded AABox bound culls exact ties, aabb.rs:26)
+            const auto &flat = s->scene.flat;
+            for (size_t k = 0; k < flat.size() && !tie; ++k) {
+                if (int(k) == id || !flat[k]) continue;
+                if (!aabb_hit_closed(flat[k]->bounding_box(0.0, 1.0), r, h->t - 2.0 * tol, h->t + 2.0 * tol)) continue;
+                const bool medium = dynamic_cast<const ConstantMedium *>(flat[k].get()) != nullptr;
+                Hit o = medium ? flat[k]->hit(r, 0.001, INF, rng) : flat[k]->hit(r, std::fmax(0.001, h->t - tol), h->t + tol, rng);
+                if (o && std::fabs(o->t - h->t) <= tol) tie = true;
+            }
+        }
         if (prim_id) prim_id[i] = id;
         if (t) t[i] = h ? h->t : INF;
         if (normal3) {
@@ -979,7 +1109,7 @@ int32_t oracle_trace_closest(const oracle_scene *s, const rt1w_ray *rays, size_t
         if (front_face) front_face[i] = h ? uint8_t(h->front_face) : 0;
         if (uv2) uv2[2 * i] = h ? h->u : 0.0, uv2[2 * i + 1] = h ? h->v : 0.0;
         if (ambiguous) {
-            bool amb = h && std::fabs(h->t - 0.001) < 1e-4;
+            bool amb = tie || (h && std::fabs(h->t - 0.001) < 1e-9);
             double dlen = magnitude(r.direction);
             const double eo = rel * std::fmax(extent, 1.0), ed = rel * dlen;
             for (int k = 0; k < 8 && !amb; ++k) {

@@ -35,9 +35,10 @@ int32_t oracle_scene_num_prims(const oracle_scene *s);
 void oracle_scene_bvh_shape(const oracle_scene *s, int32_t *n_nodes, int32_t *depth);
 
 /* world.hit(ray, 0.001, inf) for n rays (f32 inputs widened to f64).  Media replay the
- * device's keyed Philox free-flight draw.  ambiguous[i] != 0 when the winning primitive
- * changes under a 2e-6-relative perturbation of the ray (an f32 kernel cannot be held to
- * bit-exact ids there) or the hit lies within 1e-4 of t_min. */
+ * device's keyed Philox free-flight draw.  ambiguous[i] != 0 on genuine (near-)ties only: two
+ * leaves within 1e-9 relative of the winning t (e.g. the Cornell box bottom on the floor — the
+ * reference's winner depends on its random BVH order there, bvh.rs:39-46,84), a candidate within
+ * 1e-9 of t_min / t_max, or a winner that changes under a 1e-9-relative perturbation of the ray. */
 int32_t oracle_trace_closest(const oracle_scene *s, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id,
                              double *t, double *normal3, uint8_t *front_face, double *uv2, uint8_t *ambiguous,
                              int32_t threads);

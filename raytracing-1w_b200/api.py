@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = range(6)
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC, MAT_NONE = range(6)
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE, TEX_PERLIN = range(5)
 FLAG_STATS = 1
+FLAG_PROFILE = 2
 
 SCENE_IDS = {"random_scene": 0, "two_spheres": 1, "two_perlin_spheres": 2, "earth": 3, "simple_light": 4,
              "cornel_box": 5, "cornel_smoke": 6, "final_scene": 7, "stress": 8, "one_weekend": 9}
@@ -70,9 +71,13 @@ class RenderParams(C.Structure):
                 ("stat_clamp", C.c_double), ("pool_paths", C.c_int32), ("reserved", C.c_int32)]
 
 
+KERNEL_NAMES = ["generate", "extend", "shade_lambertian", "shade_metal", "shade_dielectric", "shade_diffuse_light",
+                "shade_isotropic"]  # slot = 2 + rt1w_material_type for the shade kernels
+
+
 class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("waves", C.c_uint64), ("launches", C.c_uint64),
-                ("render_ms", C.c_double), ("extend_ms", C.c_double), ("nan_samples", C.c_uint64)]
+                ("render_ms", C.c_double), ("kernel_ms", C.c_double * 7), ("kernel_launches", C.c_uint64 * 7)]
 
 
 class SceneInfo(C.Structure):

@@ -1,0 +1,402 @@
+// api.cu — the C ABI of include/rt1w.h: handles, scene commit (lowering + SAH build + upload),
+// render entry points, the closest-hit parity hook and the host-side output quantisation.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rt1w.h"
+#include "bvh.h"
+#include "lower.h"
+#include "render.h"
+
+using namespace rt1w;
+
+namespace {
+
+thread_local std::string g_error;
+
+rt1w_status fail(rt1w_status s, const std::string &msg) {
+    g_error = msg;
+    return s;
+}
+rt1w_status fail_cuda(const char *what, cudaError_t e) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return RT1W_ERR_CUDA;
+}
+
+#define RT1W_CUDA(call)                                                                                                                               \
+    do {                                                                                                                                              \
+        cudaError_t e__ = (call);                                                                                                                     \
+        if (e__ != cudaSuccess) return fail_cuda(#call, e__);                                                                                         \
+    } while (0)
+
+constexpr uint32_t kDefaultPool = 1u << 20;
+constexpr int kMaxLeaf = 2;
+
+template <class T> cudaError_t upload(const std::vector<T> &v, T **out) {
+    *out = nullptr;
+    const size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(out), bytes);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(*out, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+    return e;
+}
+
+} // namespace
+
+struct rt1w_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Pool pool;
+    Counters *h_ctr = nullptr; // pinned
+    float *d_accum = nullptr, *d_stat = nullptr;
+    size_t accum_pixels = 0, stat_pixels = 0;
+    std::mutex lock; // calls on one context are serialised (rt1w.h "Threading")
+};
+
+struct rt1w_scene {
+    rt1w_context *ctx = nullptr;
+    std::vector<rt1w_flat_prim> prims; // primitive-id order
+    rt1w_scene_info info{};
+    SceneView view{};
+    int material_mask = 0;
+    // device allocations
+    float4 *d_nodes = nullptr;
+    DPrim *d_prims = nullptr;
+    int32_t *d_prim_id = nullptr;
+    DFrame *d_frames = nullptr;
+    DMaterial *d_materials = nullptr;
+    DTexture *d_textures = nullptr;
+    DPerlin *d_perlins = nullptr;
+    cudaTextureObject_t *d_images = nullptr;
+    int2 *d_image_dims = nullptr;
+    DLight *d_lights = nullptr;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> tex_objects;
+};
+
+static void scene_release(rt1w_scene *s) {
+    if (!s) return;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
+    for (auto a : s->arrays) cudaFreeArray(a);
+    cudaFree(s->d_nodes), cudaFree(s->d_prims), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
+    cudaFree(s->d_textures), cudaFree(s->d_perlins), cudaFree(s->d_images), cudaFree(s->d_image_dims), cudaFree(s->d_lights);
+    delete s;
+}
+
+extern "C" {
+
+int32_t rt1w_abi_version(void) { return RT1W_ABI_VERSION; }
+
+const char *rt1w_last_error(void) { return g_error.c_str(); }
+
+rt1w_status rt1w_context_create(int32_t device_id, rt1w_context **out) {
+    if (!out) return fail(RT1W_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(RT1W_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    }
+    if (device_id < 0 || device_id >= count) return fail(RT1W_ERR_INVALID, "device id out of range");
+    cudaDeviceProp prop;
+    RT1W_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10) return fail(RT1W_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+    RT1W_CUDA(cudaSetDevice(device_id));
+    auto ctx = std::make_unique<rt1w_context>();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    RT1W_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RT1W_CUDA(cudaEventCreate(&ctx->ev0));
+    RT1W_CUDA(cudaEventCreate(&ctx->ev1));
+    RT1W_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_ctr), sizeof(Counters)));
+    *out = ctx.release();
+    return RT1W_OK;
+}
+
+void rt1w_context_destroy(rt1w_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    pool_free(ctx->pool);
+    cudaFree(ctx->d_accum), cudaFree(ctx->d_stat);
+    cudaFreeHost(ctx->h_ctr);
+    cudaEventDestroy(ctx->ev0), cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+rt1w_status rt1w_lower_prims(const rt1w_scene_desc *desc, rt1w_flat_prim *out, int32_t capacity, int32_t *n_out) {
+    LoweredScene low;
+    std::string err;
+    rt1w_status st = lower_scene(desc, low, err);
+    if (st != RT1W_OK) return fail(st, err);
+    if (n_out) *n_out = int32_t(low.prims.size());
+    if (out)
+        for (int32_t i = 0; i < capacity && i < int32_t(low.prims.size()); ++i) out[i] = low.prims[i];
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt1w_scene **out) {
+    if (!ctx || !out) return fail(RT1W_ERR_INVALID, "null context or output pointer");
+    *out = nullptr;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    const auto t0 = std::chrono::steady_clock::now();
+    LoweredScene low;
+    std::string err;
+    rt1w_status st = lower_scene(desc, low, err);
+    if (st != RT1W_OK) return fail(st, err);
+
+    const size_t n = low.prims.size();
+    std::vector<double> bmin(3 * n), bmax(3 * n);
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            bmin[3 * i + k] = low.prims[i].bbox_min[k], bmax[3 * i + k] = low.prims[i].bbox_max[k];
+            if (!std::isfinite(bmin[3 * i + k]) || !std::isfinite(bmax[3 * i + k]))
+                return fail(RT1W_ERR_INVALID, "No bounding box in bvh_node constructor. (bvh.rs:65-67): non-finite primitive bounds");
+        }
+    BvhBuildResult bvh;
+    build_sah_bvh(bmin.data(), bmax.data(), n, kMaxLeaf, bvh);
+    if (bvh.depth > kStackSmem + kStackLocal - 2) return fail(RT1W_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+    std::vector<DPrim> dprims(n);
+    std::vector<int32_t> prim_id(n);
+    for (size_t i = 0; i < n; ++i) {
+        dprims[i] = make_device_prim(low.prims[bvh.prim_order[i]], low.materials);
+        prim_id[i] = int32_t(bvh.prim_order[i]);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<rt1w_scene, void (*)(rt1w_scene *)> s(new rt1w_scene(), scene_release);
+    s->ctx = ctx;
+    static_assert(sizeof(BvhNode32) == 2 * sizeof(float4), "node layout");
+    RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
+    RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
+    RT1W_CUDA(upload(dprims, &s->d_prims));
+    RT1W_CUDA(upload(prim_id, &s->d_prim_id));
+    RT1W_CUDA(upload(low.frames, &s->d_frames));
+    RT1W_CUDA(upload(low.materials, &s->d_materials));
+    RT1W_CUDA(upload(low.textures, &s->d_textures));
+    RT1W_CUDA(upload(low.perlins, &s->d_perlins));
+    RT1W_CUDA(upload(low.lights, &s->d_lights));
+    // images -> CUDA texture objects (point sampled, normalised-float reads give texel/255 as texture.rs:81-87)
+    std::vector<int2> dims;
+    for (const LoweredImage &im : low.images) {
+        std::vector<uchar4> rgba(size_t(im.width) * im.height);
+        for (size_t p = 0; p < rgba.size(); ++p) rgba[p] = make_uchar4(im.rgb8[3 * p], im.rgb8[3 * p + 1], im.rgb8[3 * p + 2], 255);
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        RT1W_CUDA(cudaMallocArray(&arr, &fmt, size_t(im.width), size_t(im.height)));
+        s->arrays.push_back(arr);
+        RT1W_CUDA(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), size_t(im.width) * 4, size_t(im.width) * 4, size_t(im.height), cudaMemcpyHostToDevice));
+        cudaResourceDesc res;
+        std::memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        RT1W_CUDA(cudaCreateTextureObject(&tex, &res, &td, nullptr));
+        s->tex_objects.push_back(tex);
+        dims.push_back(make_int2(im.width, im.height));
+    }
+    RT1W_CUDA(upload(s->tex_objects, &s->d_images));
+    RT1W_CUDA(upload(dims, &s->d_image_dims));
+    const auto t2 = std::chrono::steady_clock::now();
+
+    SceneView &v = s->view;
+    v.nodes = s->d_nodes, v.prims = s->d_prims, v.prim_id = s->d_prim_id, v.frames = s->d_frames;
+    v.materials = s->d_materials, v.textures = s->d_textures, v.perlins = s->d_perlins;
+    v.images = s->d_images, v.image_dims = s->d_image_dims, v.lights = s->d_lights;
+    v.n_lights = int32_t(low.lights.size()), v.has_lights = low.has_lights ? 1 : 0;
+    v.n_prims = int32_t(n), v.n_nodes = int32_t(bvh.nodes.size()), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
+    s->material_mask = low.material_mask;
+    s->prims = low.prims;
+    s->info.n_prims = int32_t(n), s->info.n_bvh_nodes = int32_t(bvh.nodes.size()), s->info.n_frames = int32_t(low.frames.size());
+    s->info.n_lights = int32_t(low.lights.size()), s->info.bvh_depth = bvh.depth, s->info.material_mask = low.material_mask;
+    s->info.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    s->info.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    s->info.sah_cost = bvh.sah_cost;
+    *out = s.release();
+    return RT1W_OK;
+}
+
+void rt1w_scene_destroy(rt1w_scene *scene) { scene_release(scene); }
+
+rt1w_status rt1w_scene_get_info(const rt1w_scene *scene, rt1w_scene_info *out) {
+    if (!scene || !out) return fail(RT1W_ERR_INVALID, "null scene or output pointer");
+    *out = scene->info;
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_scene_get_prims(const rt1w_scene *scene, rt1w_flat_prim *out, int32_t capacity, int32_t *n_out) {
+    if (!scene) return fail(RT1W_ERR_INVALID, "null scene");
+    if (n_out) *n_out = int32_t(scene->prims.size());
+    if (out)
+        for (int32_t i = 0; i < capacity && i < int32_t(scene->prims.size()); ++i) out[i] = scene->prims[i];
+    return RT1W_OK;
+}
+
+static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *d_accum, float *d_stat,
+                                 cudaStream_t stream, rt1w_render_stats *stats) {
+    rt1w_context *ctx = scene->ctx;
+    const rt1w_render_params &p = *params;
+    if (p.width <= 0 || p.height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
+    if (p.sample_end <= p.sample_begin || p.sample_begin < 0) return fail(RT1W_ERR_INVALID, "empty sample range");
+    if (p.sample_end - p.sample_begin >= (1 << 24)) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^24-1 samples per pixel in one call");
+    if (p.max_depth < 0 || p.max_depth > 255) return fail(RT1W_ERR_UNSUPPORTED, "max_depth must be in [0, 255]");
+    if (uint64_t(p.width) * uint64_t(p.height) >= (1ull << 31)) return fail(RT1W_ERR_UNSUPPORTED, "image too large");
+    const uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
+    if (ctx->pool.capacity != want_pool) {
+        cudaError_t e = pool_alloc(ctx->pool, want_pool);
+        if (e != cudaSuccess) return fail_cuda("path pool allocation", e);
+    }
+    RenderArgs args;
+    args.sc = scene->view;
+    args.pool = ctx->pool;
+    DRenderParams &rp = args.rp;
+    rp.width = p.width, rp.height = p.height, rp.sample_begin = p.sample_begin, rp.n_samples = p.sample_end - p.sample_begin;
+    rp.max_depth = p.max_depth, rp.flags = p.flags, rp.seed_lo = uint32_t(p.seed), rp.seed_hi = uint32_t(p.seed >> 32);
+    for (int k = 0; k < 3; ++k) rp.background[k] = float(p.background[k]);
+    rp.stat_clamp = p.stat_clamp > 0.0 ? float(p.stat_clamp) : INFINITY;
+    rp.n_pixels = uint32_t(p.width) * uint32_t(p.height);
+    rp.total_paths = p.max_depth == 0 ? 0ull : (unsigned long long)rp.n_pixels * (unsigned long long)rp.n_samples; // depth 0: ray_color returns black at once
+    rp.pool = int32_t(want_pool);
+    DCamera &c = args.cam;
+    for (int k = 0; k < 3; ++k) {
+        c.origin[k] = camera->origin[k];
+        c.llc_rel[k] = camera->lower_left_corner[k] - camera->origin[k];
+        c.horizontal[k] = camera->horizontal[k], c.vertical[k] = camera->vertical[k];
+        c.u[k] = camera->u[k], c.v[k] = camera->v[k];
+    }
+    c.lens_radius = camera->lens_radius;
+    c.time0 = float(camera->time0), c.time1 = float(camera->time1);
+    args.accum = d_accum;
+    args.stat = d_stat;
+
+    RT1W_CUDA(cudaMemsetAsync(d_accum, 0, sizeof(float) * 3 * size_t(rp.n_pixels), stream));
+    if (d_stat) RT1W_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(float) * 6 * size_t(rp.n_pixels), stream));
+    RT1W_CUDA(cudaEventRecord(ctx->ev0, stream));
+    WaveStats ws;
+    ws.profile = (p.flags & RT1W_FLAG_PROFILE) != 0;
+    if (rp.total_paths > 0) {
+        cudaError_t e = render_waves(args, scene->material_mask, ctx->h_ctr, stream, ctx->sm_count, ws);
+        if (e != cudaSuccess) return fail_cuda("wavefront render", e);
+    }
+    RT1W_CUDA(cudaEventRecord(ctx->ev1, stream));
+    RT1W_CUDA(cudaStreamSynchronize(stream));
+    if (stats) {
+        float ms = 0.0f;
+        RT1W_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->paths = uint64_t(rp.n_pixels) * uint64_t(rp.n_samples);
+        stats->rays = ws.rays, stats->waves = ws.waves, stats->launches = ws.launches;
+        stats->render_ms = ms;
+        static_assert(RT1W_KERNEL_COUNT == K_COUNT, "kernel slot tables must agree");
+        for (int k = 0; k < K_COUNT; ++k) stats->kernel_ms[k] = ws.kernel_ms[k], stats->kernel_launches[k] = ws.kernel_launches[k];
+    }
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_render(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *out_rgb_sum, float *out_stat,
+                        rt1w_render_stats *stats) {
+    if (!scene || !camera || !params || !out_rgb_sum) return fail(RT1W_ERR_INVALID, "null argument");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    if (params->width <= 0 || params->height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
+    const size_t pixels = size_t(params->width) * size_t(params->height);
+    const bool want_stat = out_stat != nullptr;
+    if (want_stat && !(params->flags & RT1W_FLAG_STATS)) return fail(RT1W_ERR_INVALID, "out_stat needs RT1W_FLAG_STATS");
+    if (ctx->accum_pixels < pixels) {
+        cudaFree(ctx->d_accum), ctx->d_accum = nullptr, ctx->accum_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_accum), sizeof(float) * 3 * pixels));
+        ctx->accum_pixels = pixels;
+    }
+    if (want_stat && ctx->stat_pixels < pixels) {
+        cudaFree(ctx->d_stat), ctx->d_stat = nullptr, ctx->stat_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_stat), sizeof(float) * 6 * pixels));
+        ctx->stat_pixels = pixels;
+    }
+    rt1w_status st = render_common(scene, camera, params, ctx->d_accum, want_stat ? ctx->d_stat : nullptr, ctx->stream, stats);
+    if (st != RT1W_OK) return st;
+    RT1W_CUDA(cudaMemcpyAsync(out_rgb_sum, ctx->d_accum, sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_stat) RT1W_CUDA(cudaMemcpyAsync(out_stat, ctx->d_stat, sizeof(float) * 6 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_render_device(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *d_rgb_sum,
+                               void *cuda_stream, rt1w_render_stats *stats) {
+    if (!scene || !camera || !params || !d_rgb_sum) return fail(RT1W_ERR_INVALID, "null argument");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    if (params->flags & RT1W_FLAG_STATS) return fail(RT1W_ERR_INVALID, "RT1W_FLAG_STATS is only available through rt1w_render");
+    return render_common(scene, camera, params, d_rgb_sum, nullptr, static_cast<cudaStream_t>(cuda_stream), stats);
+}
+
+rt1w_status rt1w_trace_closest(rt1w_scene *scene, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, float *t, float *normal3,
+                               uint8_t *front_face, float *uv2) {
+    if (!scene || (!rays && n)) return fail(RT1W_ERR_INVALID, "null argument");
+    if (n == 0) return RT1W_OK;
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    struct Buffers {
+        rt1w_ray *rays = nullptr;
+        int32_t *prim = nullptr;
+        float *t = nullptr, *normal = nullptr, *uv = nullptr;
+        uint8_t *ff = nullptr;
+        ~Buffers() { cudaFree(rays), cudaFree(prim), cudaFree(t), cudaFree(normal), cudaFree(uv), cudaFree(ff); }
+    } b;
+    RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&b.rays), sizeof(rt1w_ray) * n));
+    RT1W_CUDA(cudaMemcpyAsync(b.rays, rays, sizeof(rt1w_ray) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (prim_id) RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&b.prim), sizeof(int32_t) * n));
+    if (t) RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&b.t), sizeof(float) * n));
+    if (normal3) RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&b.normal), sizeof(float) * 3 * n));
+    if (uv2) RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&b.uv), sizeof(float) * 2 * n));
+    if (front_face) RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&b.ff), n));
+    RT1W_CUDA(trace_closest_launch(scene->view, b.rays, n, seed, b.prim, b.t, b.normal, b.ff, b.uv, ctx->stream));
+    if (prim_id) RT1W_CUDA(cudaMemcpyAsync(prim_id, b.prim, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t) RT1W_CUDA(cudaMemcpyAsync(t, b.t, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal3) RT1W_CUDA(cudaMemcpyAsync(normal3, b.normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uv2) RT1W_CUDA(cudaMemcpyAsync(uv2, b.uv, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (front_face) RT1W_CUDA(cudaMemcpyAsync(front_face, b.ff, n, cudaMemcpyDeviceToHost, ctx->stream));
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+void rt1w_resolve_rgb8(const float *rgb_sum, int32_t width, int32_t height, int32_t samples_per_pixel, uint8_t *out_rgb8) {
+    // color.rs:14-21 (NaN sum -> 0, then * 1/spp) and color.rs:56-65 (gamma 2, clamp to [0, 0.999], * 256, truncate)
+    const double scale = 1.0 / double(samples_per_pixel);
+    const size_t n = size_t(width) * size_t(height) * 3;
+    for (size_t i = 0; i < n; ++i) {
+        double x = double(rgb_sum[i]);
+        if (std::isnan(x)) x = 0.0;
+        x *= scale;
+        double g = std::sqrt(x);
+        g = g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g);
+        const double q = 256.0 * g;
+        out_rgb8[i] = std::isnan(q) ? uint8_t(0) : uint8_t(int(q));
+    }
+}
+
+void rt1w_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    const Philox4 r = philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1]);
+    out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
+}
+
+} // extern "C"

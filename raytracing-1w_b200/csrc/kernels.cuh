@@ -1,0 +1,620 @@
+// kernels.cuh — device code of the wavefront path tracer (sm_100a).
+//
+// Everything the reference does per ray inside `ray_color` (main.rs:51-190) lives here as
+// __device__ functions; render.cu wraps them into the wavefront kernels
+// (generate / extend / shade_<material>) and the closest-hit parity kernel.
+//
+// Precision policy (DESIGN.md "Precision"): the reference is f64 throughout (main.rs:1).
+//   * BVH node slab tests: f32 on conservatively padded boxes (bvh.cpp store_box).
+//   * primitive intersection, hit position, wrapper transforms: f64 (B200 issues DFMA at half the
+//     FFMA rate; this keeps hit distances bit-close to the reference and removes every f32
+//     self-intersection artefact of 555-unit scenes with t_min = 0.001).
+//   * directions, normals, pdfs, throughput, textures, radiance sums: f32.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "philox.h"
+
+namespace rt1w {
+
+#define RT1W_DEV __device__ __forceinline__
+
+constexpr double kTMin = 0.001;      // main.rs:62
+constexpr float kPiF = 3.14159265358979323846f;
+constexpr int kStackSmem = 24;       // per-thread short stack entries kept in shared memory
+constexpr int kStackLocal = 40;      // overflow entries (local memory; the builder caps the depth at 62)
+
+struct SceneView {
+    const float4 *nodes;       // 2 x float4 per node
+    const DPrim *prims;        // leaf order
+    const int32_t *prim_id;    // leaf index -> primitive id (DFS order of the description)
+    const DFrame *frames;
+    const DMaterial *materials;
+    const DTexture *textures;
+    const DPerlin *perlins;
+    const cudaTextureObject_t *images;
+    const int2 *image_dims;
+    const DLight *lights;
+    int32_t n_lights, has_lights;
+    int32_t n_prims, n_nodes, n_perlins, n_frames;
+};
+
+struct f3 {
+    float x, y, z;
+};
+struct d3 {
+    double x, y, z;
+};
+RT1W_DEV f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+RT1W_DEV f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+RT1W_DEV f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+RT1W_DEV f3 operator-(f3 a) { return f3{-a.x, -a.y, -a.z}; }
+RT1W_DEV f3 operator*(float s, f3 a) { return f3{s * a.x, s * a.y, s * a.z}; }
+RT1W_DEV f3 operator*(f3 a, f3 b) { return f3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+RT1W_DEV float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RT1W_DEV f3 cross(f3 a, f3 b) { return f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+RT1W_DEV f3 normalize(f3 a) { return rsqrtf(dot(a, a)) * a; }
+
+// ------------------------------------------------------------------------------------------
+// Ray + path state as the kernels see them (SoA in HBM, see Pool in render.cu)
+// ------------------------------------------------------------------------------------------
+struct Ray {
+    double ox, oy, oz;
+    float dx, dy, dz;
+    float time;
+};
+
+struct __align__(16) RayB { // second 16-byte word of a ray slot
+    double oz;
+    float dx, dy;
+};
+struct __align__(16) RayC { // third word: rest of the ray + the path bookkeeping
+    float dz, time;
+    uint32_t state; // (sample - sample_begin) << 8 | depth
+    uint32_t pixel; // row * width + column, row 0 = top
+};
+struct __align__(16) HitRec {
+    double t;
+    int32_t leaf; // index into SceneView::prims (leaf order)
+    uint32_t pad;
+};
+
+// How ConstantMedium candidates draw their free-flight number (constant_medium.rs:85).
+// counter = (c0, c1, c2, id), key = (k0, k1); `exact` selects the f64 logarithm and the
+// primitive-id keyed counter that the CPU checker replays (rt1w.h: rt1w_trace_closest).
+struct MediumRng {
+    uint32_t c0, c1, c2, k0, k1;
+};
+
+// ------------------------------------------------------------------------------------------
+// Wrapper chains
+// ------------------------------------------------------------------------------------------
+struct LocalRay {
+    double ox, oy, oz, dx, dy, dz;
+};
+
+RT1W_DEV LocalRay to_local(const SceneView &sc, int frame, const Ray &r) {
+    LocalRay l;
+    if (frame < 0) {
+        l.ox = r.ox, l.oy = r.oy, l.oz = r.oz, l.dx = r.dx, l.dy = r.dy, l.dz = r.dz;
+        return l;
+    }
+    const DFrame *f = sc.frames + frame; // hittable.rs:207 and :241-245, composed on the host
+    const double s = f->sin_t, c = f->cos_t;
+    l.ox = c * r.ox - s * r.oz + f->bx;
+    l.oy = r.oy + f->by;
+    l.oz = s * r.ox + c * r.oz + f->bz;
+    l.dx = c * double(r.dx) - s * double(r.dz);
+    l.dy = r.dy;
+    l.dz = s * double(r.dx) + c * double(r.dz);
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------
+// Primitive tests (f64).  Each returns the accepted root in [tmin, tmax] like the reference.
+// ------------------------------------------------------------------------------------------
+RT1W_DEV bool sphere_roots(const LocalRay &l, double cx, double cy, double cz, double radius, double &r0, double &r1) {
+    // sphere.rs:31-41
+    const double ocx = l.ox - cx, ocy = l.oy - cy, ocz = l.oz - cz;
+    const double a = l.dx * l.dx + l.dy * l.dy + l.dz * l.dz;
+    const double half_b = ocx * l.dx + ocy * l.dy + ocz * l.dz;
+    const double c = ocx * ocx + ocy * ocy + ocz * ocz - radius * radius;
+    const double disc = half_b * half_b - a * c;
+    if (disc < 0.0) return false;
+    const double sqrtd = sqrt(disc);
+    const double inv_a = 1.0 / a;
+    r0 = (-half_b - sqrtd) * inv_a;
+    r1 = (-half_b + sqrtd) * inv_a;
+    return true;
+}
+
+RT1W_DEV bool hit_sphere(const LocalRay &l, double cx, double cy, double cz, double radius, double tmin, double tmax, double &t) {
+    double r0, r1;
+    if (!sphere_roots(l, cx, cy, cz, radius, r0, r1)) return false;
+    double root = r0; // sphere.rs:43-48: near root first, then far
+    if (root < tmin || tmax < root) {
+        root = r1;
+        if (root < tmin || tmax < root) return false;
+    }
+    t = root;
+    return true;
+}
+
+// rect with constant axis AX (0: YZRect, 1: XZRect, 2: XYRect); aarect.rs:46-72,84-110,152-178
+template <int AX> RT1W_DEV bool hit_rect(const LocalRay &l, double a0, double a1, double b0, double b1, double k, double tmin, double tmax, double &t) {
+    const double oc = AX == 0 ? l.ox : (AX == 1 ? l.oy : l.oz);
+    const double dc = AX == 0 ? l.dx : (AX == 1 ? l.dy : l.dz);
+    const double oa = AX == 0 ? l.oy : l.ox, da = AX == 0 ? l.dy : l.dx;
+    const double ob = AX == 2 ? l.oy : l.oz, db = AX == 2 ? l.dy : l.dz;
+    const double tt = (k - oc) / dc;
+    if (tt < tmin || tt > tmax) return false;
+    const double a = oa + tt * da, b = ob + tt * db;
+    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+    t = tt;
+    return true;
+}
+
+template <bool EXACT>
+RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, double ray_length, double tmin, double tmax,
+                            const MediumRng &mr, uint32_t id, double &t) {
+    // constant_medium.rs:74-104 given the two boundary hits
+    double t1 = fmax(t_in, tmin), t2 = fmin(t_out, tmax);
+    if (t1 >= t2) return false;
+    t1 = fmax(t1, 0.0);
+    const double inside = (t2 - t1) * ray_length;
+    const Philox4 x = philox4x32_10(mr.c0, mr.c1, mr.c2, id, mr.k0, mr.k1);
+    const float xi = u01(x.x);
+    const double hit_distance = EXACT ? neg_inv_density * log(double(xi)) : neg_inv_density * double(__logf(xi));
+    if (hit_distance > inside) return false;
+    t = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// One candidate primitive.  Returns true and the hit parameter when it beats (tmin, tmax].
+template <bool EXACT> RT1W_DEV bool hit_prim(const SceneView &sc, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
+    const double2 *w = reinterpret_cast<const double2 *>(sc.prims + leaf);
+    const int4 tail = __ldg(reinterpret_cast<const int4 *>(w + 3)); // q2 | meta | frame
+    const uint32_t meta = uint32_t(tail.z);
+    const int type = int(meta & 15u);
+    const double2 p01 = __ldg(w), p23 = __ldg(w + 1);
+    const LocalRay l = to_local(sc, tail.w, r);
+    switch (type) {
+    case P_SPHERE: return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
+    case P_MOVING_SPHERE: { // moving_sphere.rs:23-26,31-48
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(w + 2));
+        const double s = double((r.time - f.w) * __int_as_float(tail.x));
+        return hit_sphere(l, p01.x + s * double(f.x), p01.y + s * double(f.y), p23.x + s * double(f.z), p23.y, kTMin, tmax, t);
+    }
+    case P_XY_RECT: return hit_rect<2>(l, p01.x, p01.y, p23.x, p23.y, __ldg(reinterpret_cast<const double *>(w + 2)), kTMin, tmax, t);
+    case P_XZ_RECT: return hit_rect<1>(l, p01.x, p01.y, p23.x, p23.y, __ldg(reinterpret_cast<const double *>(w + 2)), kTMin, tmax, t);
+    case P_YZ_RECT: return hit_rect<0>(l, p01.x, p01.y, p23.x, p23.y, __ldg(reinterpret_cast<const double *>(w + 2)), kTMin, tmax, t);
+    case P_MEDIUM_SPHERE: { // boundary.hit(-inf, inf) then boundary.hit(t1 + 0.0001, inf), constant_medium.rs:58-72
+        double r0, r1;
+        if (!sphere_roots(l, p01.x, p01.y, p23.x, p23.y, r0, r1)) return false;
+        if (r1 < r0 + 0.0001) return false;
+        const double nid = __ldg(reinterpret_cast<const double *>(w + 2));
+        const double len = sqrt(l.dx * l.dx + l.dy * l.dy + l.dz * l.dz);
+        const uint32_t id = EXACT ? uint32_t(__ldg(sc.prim_id + leaf)) : uint32_t(leaf);
+        return medium_sample<EXACT>(r0, r1, nid, len, kTMin, tmax, mr, id, t);
+    }
+    case P_MEDIUM_BOX: { // the six sides of aabox.rs:29-76 as three slabs
+        const double2 q01 = __ldg(w + 2);
+        const double q2 = __hiloint2double(tail.y, tail.x);
+        const double ix = 1.0 / l.dx, iy = 1.0 / l.dy, iz = 1.0 / l.dz;
+        double ax = (p01.x - l.ox) * ix, bx = (q01.x - l.ox) * ix;
+        double ay = (p01.y - l.oy) * iy, by = (q01.y - l.oy) * iy;
+        double az = (p23.x - l.oz) * iz, bz = (q2 - l.oz) * iz;
+        const double t_in = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmin(az, bz));
+        const double t_out = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmax(az, bz));
+        if (!(t_in <= t_out)) return false;
+        if (t_out < t_in + 0.0001) return false;
+        const double len = sqrt(l.dx * l.dx + l.dy * l.dy + l.dz * l.dz);
+        const uint32_t id = EXACT ? uint32_t(__ldg(sc.prim_id + leaf)) : uint32_t(leaf);
+        return medium_sample<EXACT>(t_in, t_out, p23.y, len, kTMin, tmax, mr, id, t);
+    }
+    default: return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// extend: closest hit over the flat SAH BVH (replaces BVHNode::hit, bvh.rs:25-50)
+// ------------------------------------------------------------------------------------------
+struct SlabRay {
+    float ox, oy, oz, ix, iy, iz;
+};
+
+RT1W_DEV bool slab(const float4 lo, const float4 hi, const SlabRay &s, float tmax, float &tnear) {
+    const float ax = (lo.x - s.ox) * s.ix, bx = (hi.x - s.ox) * s.ix;
+    const float ay = (lo.y - s.oy) * s.iy, by = (hi.y - s.oy) * s.iy;
+    const float az = (lo.z - s.oz) * s.iz, bz = (hi.z - s.oz) * s.iz;
+    // fminf/fmaxf drop NaNs (0 * inf on an axis-parallel ray grazing a slab plane)
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    tf = tf * 1.0000005f; // keep the f32 test conservative w.r.t. the f64 primitive solve
+    tnear = tn;
+    return tn <= tf;
+}
+
+// `stack` points at this thread's column of the shared short stack (stride = blockDim.x).
+template <bool EXACT>
+RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr, uint32_t *stack, int stride, double &t_best, int &leaf_best) {
+    SlabRay s;
+    s.ox = float(r.ox), s.oy = float(r.oy), s.oz = float(r.oz);
+    s.ix = 1.0f / r.dx, s.iy = 1.0f / r.dy, s.iz = 1.0f / r.dz;
+    double best = CUDART_INF;
+    float bestf = CUDART_INF_F;
+    int best_leaf = -1;
+    uint32_t overflow[kStackLocal];
+    int sp = 0;
+    uint32_t node = 0;
+    {
+        float tn;
+        if (!slab(__ldg(sc.nodes), __ldg(sc.nodes + 1), s, bestf, tn)) {
+            t_best = best, leaf_best = -1;
+            return false;
+        }
+    }
+    for (;;) {
+        const float4 n0 = __ldg(sc.nodes + 2 * node), n1 = __ldg(sc.nodes + 2 * node + 1);
+        const uint32_t left_first = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
+        bool pop = true;
+        if (count == 0) {
+            const float4 *c = sc.nodes + 2 * left_first;
+            const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
+            float tl, tr;
+            const bool hl = slab(l0, l1, s, bestf, tl), hr = slab(r0, r1, s, bestf, tr);
+            if (hl && hr) {
+                const bool left_first_order = tl <= tr;
+                const uint32_t near_n = left_first_order ? left_first : left_first + 1;
+                const uint32_t far_n = left_first_order ? left_first + 1 : left_first;
+                if (sp < kStackSmem) stack[sp * stride] = far_n;
+                else overflow[sp - kStackSmem] = far_n;
+                ++sp;
+                node = near_n;
+                pop = false;
+            } else if (hl || hr) {
+                node = hl ? left_first : left_first + 1;
+                pop = false;
+            }
+        } else {
+            for (uint32_t i = 0; i < count; ++i) {
+                double t;
+                if (hit_prim<EXACT>(sc, int(left_first + i), r, best, mr, t)) {
+                    best = t, best_leaf = int(left_first + i);
+                    bestf = __double2float_ru(t);
+                }
+            }
+        }
+        if (pop) {
+            // skip stacked subtrees that the current best already culls is left to the slab test on pop
+            if (sp == 0) break;
+            --sp;
+            node = sp < kStackSmem ? stack[sp * stride] : overflow[sp - kStackSmem];
+        }
+    }
+    t_best = best, leaf_best = best_leaf;
+    return best_leaf >= 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// HitRecord reconstruction (hittable.rs:10-47 + the wrapper rewrites)
+// ------------------------------------------------------------------------------------------
+struct HitInfo {
+    double px, py, pz; // position
+    f3 normal;         // oriented normal as the material sees it
+    f3 n_out;          // outward unit normal in the leaf's own space (sphere_uv input)
+    float u, v;
+    bool front_face;
+    int type; // PrimType
+    uint32_t meta;
+};
+
+RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
+    // theta = acos(-y), written as atan2(|xz|, -y): identical for a unit vector but well conditioned
+    // at the poles, where acos would amplify the f32 rounding of y to 1e-4
+    const float theta = atan2f(sqrtf(p.x * p.x + p.z * p.z), -p.y);
+    const float phi = atan2f(-p.z, p.x) + kPiF;
+    u = phi * (0.5f / kPiF), v = theta * (1.0f / kPiF);
+}
+
+template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const SceneView &sc, int leaf, const Ray &r, double t) {
+    HitInfo h;
+    const double2 *w = reinterpret_cast<const double2 *>(sc.prims + leaf);
+    const int4 tail = __ldg(reinterpret_cast<const int4 *>(w + 3));
+    h.meta = uint32_t(tail.z);
+    h.type = int(h.meta & 15u);
+    const int frame = tail.w;
+    // ray.at(t) is invariant under the rigid wrappers; evaluate it once in world space
+    h.px = r.ox + t * double(r.dx), h.py = r.oy + t * double(r.dy), h.pz = r.oz + t * double(r.dz);
+    h.u = 0.0f, h.v = 0.0f;
+    if (h.type == P_MEDIUM_SPHERE || h.type == P_MEDIUM_BOX) { // constant_medium.rs:104-112
+        h.normal = h.n_out = mk3(1.0f, 0.0f, 0.0f);
+        h.front_face = true;
+    } else {
+        const LocalRay l = to_local(sc, frame, r);
+        const double lx = l.ox + t * l.dx, ly = l.oy + t * l.dy, lz = l.oz + t * l.dz;
+        const double2 p01 = __ldg(w), p23 = __ldg(w + 1);
+        f3 n;
+        if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
+            double cx = p01.x, cy = p01.y, cz = p23.x;
+            if (h.type == P_MOVING_SPHERE) {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(w + 2));
+                const double s = double((r.time - f.w) * __int_as_float(tail.x));
+                cx += s * double(f.x), cy += s * double(f.y), cz += s * double(f.z);
+            }
+            const double inv_r = 1.0 / p23.y; // sphere.rs:51
+            n = mk3(float((lx - cx) * inv_r), float((ly - cy) * inv_r), float((lz - cz) * inv_r));
+            if (WANT_UV) sphere_uv(n, h.u, h.v);
+        } else {
+            double a, b;
+            if (h.type == P_XY_RECT) n = mk3(0.0f, 0.0f, 1.0f), a = lx, b = ly;
+            else if (h.type == P_XZ_RECT) n = mk3(0.0f, 1.0f, 0.0f), a = lx, b = lz;
+            else n = mk3(1.0f, 0.0f, 0.0f), a = ly, b = lz;
+            if (WANT_UV) { // aarect.rs:60-61
+                h.u = float((a - p01.x) / (p01.y - p01.x));
+                h.v = float((b - p23.x) / (p23.y - p23.x));
+            }
+        }
+        h.n_out = n;
+        // HitRecord::new at the leaf, with the leaf-space ray (hittable.rs:30-35)
+        bool ff = (l.dx * double(n.x) + l.dy * double(n.y) + l.dz * double(n.z)) < 0.0;
+        if (!ff) n = -n;
+        if (frame >= 0) {
+            const DFrame *f = sc.frames + frame;
+            const int n_ops = f->n_ops;
+            for (int i = 0; i < n_ops; ++i) { // innermost wrapper first
+                const DChainOp op = f->ops[i];
+                if (op.kind == OP_FLIP_FACE) { // hittable.rs:290-294
+                    ff = !ff;
+                    continue;
+                }
+                if (op.kind == OP_ROTATE_Y) { // hittable.rs:263-267
+                    const float nx = op.cos_own * n.x + op.sin_own * n.z;
+                    const float nz = -op.sin_own * n.x + op.cos_own * n.z;
+                    n.x = nx, n.z = nz;
+                }
+                // both wrappers re-run HitRecord::new with the ray INSIDE the wrapper (hittable.rs:221-229,269-277)
+                const float dx = op.cos_cum * r.dx - op.sin_cum * r.dz;
+                const float dz = op.sin_cum * r.dx + op.cos_cum * r.dz;
+                ff = (dx * n.x + r.dy * n.y + dz * n.z) < 0.0f;
+                if (!ff) n = -n;
+            }
+        } else if ((h.meta >> 4) & PF_FLIP_FACE) {
+            ff = !ff;
+        }
+        h.normal = n;
+        h.front_face = ff;
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// Textures (texture.rs, perlin.rs)
+// ------------------------------------------------------------------------------------------
+RT1W_DEV float perlin_noise(const DPerlin *tab, double px, double py, double pz) { // perlin.rs:46-72,88-106
+    const double fx = floor(px), fy = floor(py), fz = floor(pz);
+    const float u = float(px - fx), v = float(py - fy), w = float(pz - fz);
+    const int i = int((long long)fx), j = int((long long)fy), k = int((long long)fz);
+    const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const int idx = tab->perm[0][(i + di) & 255] ^ tab->perm[1][(j + dj) & 255] ^ tab->perm[2][(k + dk) & 255];
+                const float4 c = *reinterpret_cast<const float4 *>(tab->ranvec[idx]);
+                const float wx = di ? uu : 1.0f - uu, wy = dj ? vv : 1.0f - vv, wz = dk ? ww : 1.0f - ww;
+                accum += wx * wy * wz * (c.x * (u - di) + c.y * (v - dj) + c.z * (w - dk));
+            }
+    return accum;
+}
+
+RT1W_DEV float perlin_turb(const DPerlin *tab, double px, double py, double pz, int depth) { // perlin.rs:74-86
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(tab, px, py, pz);
+        weight *= 0.5f;
+        px *= 2.0, py *= 2.0, pz *= 2.0;
+    }
+    return fabsf(accum);
+}
+
+// sin of a f64 argument through f32 after an f64 range reduction (arguments reach 1e4 in the scenes)
+RT1W_DEV float sin_reduced(double x) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const double k = rint(x * (1.0 / two_pi));
+    return sinf(float(x - k * two_pi));
+}
+
+// `perlins` may point at shared memory copies of the tables (render.cu stages them per CTA).
+RT1W_DEV f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
+    DTexture t = sc.textures[tex];
+    for (int guard = 0; guard < 9 && t.type == RT1W_TEX_CHECKER; ++guard) { // texture.rs:46-55
+        const float sines = sin_reduced(10.0 * h.px) * sin_reduced(10.0 * h.py) * sin_reduced(10.0 * h.pz);
+        t = sc.textures[sines < 0.0f ? t.odd : t.even];
+    }
+    switch (t.type) {
+    case RT1W_TEX_SOLID: return mk3(t.color[0], t.color[1], t.color[2]);
+    case RT1W_TEX_NOISE: { // texture.rs:57-65
+        const float turb = perlin_turb(perlins + t.table, h.px, h.py, h.pz, 7);
+        const float s = 0.5f * (1.0f + sin_reduced(double(t.scale) * h.pz + 10.0 * double(turb)));
+        return mk3(s, s, s);
+    }
+    case RT1W_TEX_PERLIN: { // perlin.rs:109-113
+        const float s = perlin_noise(perlins + t.table, h.px, h.py, h.pz);
+        return mk3(s, s, s);
+    }
+    case RT1W_TEX_IMAGE: { // texture.rs:67-89: nearest texel, (0,0) = top-left
+        float u = h.u, v = h.v;
+        if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) sphere_uv(h.n_out, u, v);
+        u = fminf(fmaxf(u, 0.0f), 1.0f);
+        v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+        const int2 dim = sc.image_dims[t.table];
+        const int i = min(int(u * float(dim.x)), dim.x - 1), j = min(int(v * float(dim.y)), dim.y - 1);
+        const float4 c = tex2D<float4>(sc.images[t.table], float(i) + 0.5f, float(j) + 0.5f);
+        return mk3(c.x, c.y, c.z);
+    }
+    default: return mk3(0.0f, 0.0f, 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sampling (math.rs, onb.rs, pdf.rs) on a counter-based RNG
+// ------------------------------------------------------------------------------------------
+struct Rng { // Philox4x32-10 stream: key = (pixel, seed), counter = (sample, bounce, purpose, block)
+    uint32_t k0, k1, c0, c1, c2, block;
+    RT1W_DEV Philox4 next4() { return philox4x32_10(c0, c1, c2, block++, k0, k1); }
+};
+
+struct Onb {
+    f3 u, v, w;
+};
+RT1W_DEV Onb onb_from_w(f3 n) { // onb.rs:13-24
+    Onb o;
+    o.w = normalize(n);
+    const f3 a = fabsf(o.w.x) > 0.9f ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, 0.0f, 0.0f);
+    o.v = normalize(cross(o.w, a));
+    o.u = cross(o.w, o.v);
+    return o;
+}
+RT1W_DEV f3 onb_local(const Onb &o, f3 a) { return a.x * o.u + a.y * o.v + a.z * o.w; } // onb.rs:26-28
+
+RT1W_DEV f3 random_in_unit_sphere(Rng &rng) { // math.rs:6-18 (three gen_range(-1..1) per try)
+    for (;;) {
+        const Philox4 x = rng.next4();
+        const f3 p = mk3(2.0f * u01(x.x) - 1.0f, 2.0f * u01(x.y) - 1.0f, 2.0f * u01(x.z) - 1.0f);
+        if (dot(p, p) < 1.0f) return p;
+    }
+}
+
+RT1W_DEV f3 random_cosine_direction(float r1, float r2) { // math.rs:39-49
+    const float z = sqrtf(1.0f - r2);
+    float sn, cs;
+    sincospif(2.0f * r1, &sn, &cs);
+    const float q = sqrtf(r2);
+    return mk3(cs * q, sn * q, z);
+}
+
+RT1W_DEV f3 random_to_sphere(float radius, float distance_squared, float r1, float r2) { // math.rs:51-65
+    const float z = 1.0f + r2 * (sqrtf(1.0f - radius * radius / distance_squared) - 1.0f);
+    float sn, cs;
+    sincospif(2.0f * r1, &sn, &cs);
+    const float q = sqrtf(1.0f - z * z);
+    return mk3(cs * q, sn * q, z);
+}
+
+// pdf_value of one light for the ray (o, v), hit range [0.001, inf) (aarect.rs:119-138, sphere.rs:72-90).
+RT1W_DEV float light_pdf_value(const DLight &L, double ox, double oy, double oz, f3 v) {
+    if (L.kind == L_XZ_RECT) {
+        const double t = (L.p[4] - oy) / double(v.y);
+        if (t < kTMin || t > CUDART_INF) return 0.0f; // NaN passes both comparisons, as in aarect.rs:85-88
+        const double x = ox + t * double(v.x), z = oz + t * double(v.z);
+        if (x < L.p[0] || x > L.p[1] || z < L.p[2] || z > L.p[3]) return 0.0f;
+        const float area = float((L.p[1] - L.p[0]) * (L.p[3] - L.p[2]));
+        const float len2 = dot(v, v);
+        const float tf = float(t);
+        const float distance_squared = tf * tf * len2;
+        const float cosine = fabsf(v.y * rsqrtf(len2)); // normal is +-y
+        return distance_squared / (cosine * area);
+    }
+    if (L.kind == L_SPHERE) {
+        LocalRay l;
+        l.ox = ox, l.oy = oy, l.oz = oz, l.dx = v.x, l.dy = v.y, l.dz = v.z;
+        double t;
+        if (!hit_sphere(l, L.p[0], L.p[1], L.p[2], L.p[3], kTMin, CUDART_INF, t)) return 0.0f;
+        const double cx = L.p[0] - ox, cy = L.p[1] - oy, cz = L.p[2] - oz;
+        const float d2 = float(cx * cx + cy * cy + cz * cz);
+        const float r = float(L.p[3]);
+        const float cos_theta_max = sqrtf(1.0f - r * r / d2);
+        const float solid_angle = 2.0f * kPiF * (1.0f - cos_theta_max);
+        return 1.0f / solid_angle;
+    }
+    return 0.0f; // trait default, hittable.rs:66-68
+}
+
+RT1W_DEV f3 light_random(const DLight &L, double ox, double oy, double oz, float r1, float r2) {
+    if (L.kind == L_XZ_RECT) { // aarect.rs:140-147 (un-normalised)
+        const double x = L.p[0] + (L.p[1] - L.p[0]) * double(r1);
+        const double z = L.p[2] + (L.p[3] - L.p[2]) * double(r2);
+        return mk3(float(x - ox), float(L.p[4] - oy), float(z - oz));
+    }
+    if (L.kind == L_SPHERE) { // sphere.rs:92-99
+        const f3 dir = mk3(float(L.p[0] - ox), float(L.p[1] - oy), float(L.p[2] - oz));
+        const Onb uvw = onb_from_w(dir);
+        return onb_local(uvw, random_to_sphere(float(L.p[3]), dot(dir, dir), r1, r2));
+    }
+    return mk3(1.0f, 0.0f, 0.0f); // trait default, hittable.rs:69-71
+}
+
+// ------------------------------------------------------------------------------------------
+// Materials (material.rs, constant_medium.rs:31-51).  Each returns the scattered direction and
+// multiplies the throughput; `time_out` carries the reference's time quirk (main.rs:86).
+// ------------------------------------------------------------------------------------------
+RT1W_DEV f3 reflect(f3 v, f3 n) { return v - (2.0f * dot(v, n)) * n; } // material.rs:94-96
+
+RT1W_DEV f3 refract(f3 uv, f3 n, float etai_over_etat) { // material.rs:114-119
+    const float cos_theta = fminf(dot(-uv, n), 1.0f);
+    const f3 r_out_perp = etai_over_etat * (uv + cos_theta * n);
+    const f3 r_out_parallel = (-sqrtf(fabsf(1.0f - dot(r_out_perp, r_out_perp)))) * n;
+    return r_out_perp + r_out_parallel;
+}
+
+RT1W_DEV float reflectance(float cosine, float ref_idx) { // material.rs:121-125
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    const float m = 1.0f - cosine;
+    const float m2 = m * m;
+    return r0 + (1.0f - r0) * (m2 * m2 * m);
+}
+
+// Lambertian + MixturePdf(HittablePdf(lights), CosinePdf) — main.rs:75-104 / :142-160, material.rs:70-92, pdf.rs:36-69
+RT1W_DEV f3 scatter_lambertian(const SceneView &sc, const DLight *lights, const HitInfo &h, Rng &rng, f3 &weight) {
+    const Onb uvw = onb_from_w(h.normal);
+    const Philox4 x = rng.next4();
+    f3 dir;
+    float pdf;
+    if (sc.has_lights) {
+        const int n = sc.n_lights;
+        if (x.x >> 31) { // rng.gen::<bool>() -> HittablePdf (pdf.rs:63-64)
+            const int pick = min(int(u01(x.y) * float(n)), n - 1); // slice.choose (hittable.rs:153)
+            dir = light_random(lights[pick], h.px, h.py, h.pz, u01(x.z), u01(x.w));
+        } else {
+            dir = onb_local(uvw, random_cosine_direction(u01(x.z), u01(x.w)));
+        }
+        float lsum = 0.0f;
+        const float wl = 1.0f / float(n);
+        for (int i = 0; i < n; ++i) lsum += wl * light_pdf_value(lights[i], h.px, h.py, h.pz, dir); // hittable.rs:144-150
+        const float cosine = dot(normalize(dir), uvw.w);
+        pdf = 0.5f * lsum + 0.5f * fmaxf(cosine * (1.0f / kPiF), 0.0f); // pdf.rs:58-60
+    } else {
+        dir = onb_local(uvw, random_cosine_direction(u01(x.z), u01(x.w)));
+        pdf = fmaxf(dot(normalize(dir), uvw.w) * (1.0f / kPiF), 0.0f); // pdf.rs:37-40
+    }
+    const float spdf = fmaxf(dot(h.normal, normalize(dir)) * (1.0f / kPiF), 0.0f); // material.rs:82-91
+    const float s = spdf / pdf;                                                      // unguarded, main.rs:102
+    weight = mk3(s, s, s);
+    return dir;
+}
+
+RT1W_DEV f3 scatter_metal(const DMaterial &m, const Ray &r, const HitInfo &h, Rng &rng) { // material.rs:98-112
+    const f3 reflected = reflect(normalize(mk3(r.dx, r.dy, r.dz)), h.normal);
+    return reflected + m.fuzz * random_in_unit_sphere(rng);
+}
+
+RT1W_DEV f3 scatter_dielectric(const DMaterial &m, const Ray &r, const HitInfo &h, Rng &rng) { // material.rs:132-161
+    const float ratio = h.front_face ? 1.0f / m.ir : m.ir;
+    const f3 unit = normalize(mk3(r.dx, r.dy, r.dz));
+    const float cos_theta = fminf(dot(-unit, h.normal), 1.0f);
+    const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    bool reflects = ratio * sin_theta > 1.0f;
+    if (!reflects) reflects = reflectance(cos_theta, ratio) > u01(rng.next4().x);
+    return reflects ? reflect(unit, h.normal) : refract(unit, h.normal, ratio);
+}
+
+} // namespace rt1w

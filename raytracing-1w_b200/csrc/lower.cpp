@@ -83,8 +83,8 @@ struct Walker {
         }
         DFrame f;
         std::memset(&f, 0, sizeof(f));
-        f.sin_t = float(x.s), f.cos_t = float(x.c);
-        f.bx = float(x.b[0]), f.by = float(x.b[1]), f.bz = float(x.b[2]);
+        f.sin_t = x.s, f.cos_t = x.c;
+        f.bx = x.b[0], f.by = x.b[1], f.bz = x.b[2];
         // ops: innermost first among the first `ops_upto` wrappers
         double cs = 0, cc = 1; // cumulative rotation of the direction, outermost -> inner
         std::vector<DChainOp> outer_first;
@@ -383,10 +383,10 @@ rt1w_status lower_scene(const rt1w_scene_desc *desc, LoweredScene &out, std::str
                 std::memset(&l, 0, sizeof(l));
                 if (n.type == RT1W_NODE_XZ_RECT) { // aarect.rs:119-147
                     l.kind = L_XZ_RECT;
-                    for (int k = 0; k < 5; ++k) l.p[k] = float(n.p[k]);
+                    for (int k = 0; k < 5; ++k) l.p[k] = n.p[k];
                 } else if (n.type == RT1W_NODE_SPHERE) { // sphere.rs:72-99
                     l.kind = L_SPHERE;
-                    for (int k = 0; k < 4; ++k) l.p[k] = float(n.p[k]);
+                    for (int k = 0; k < 4; ++k) l.p[k] = n.p[k];
                 } else { // trait defaults: pdf 0, direction (1,0,0) (hittable.rs:66-71); wrappers do not forward
                     l.kind = L_OTHER;
                 }
@@ -406,46 +406,39 @@ rt1w_status lower_scene(const rt1w_scene_desc *desc, LoweredScene &out, std::str
 DPrim make_device_prim(const rt1w_flat_prim &fp, const std::vector<DMaterial> &materials) {
     DPrim d;
     std::memset(&d, 0, sizeof(d));
-    float q[14] = {0};
     int type = 0;
     const double *p = fp.p;
     switch (fp.kind) {
     case RT1W_NODE_SPHERE:
         type = P_SPHERE;
-        for (int i = 0; i < 4; ++i) q[i] = float(p[i]);
+        for (int i = 0; i < 4; ++i) d.p[i] = p[i];
         break;
-    case RT1W_NODE_MOVING_SPHERE: { // re-parametrised on the scope times (see device_types.h)
+    case RT1W_NODE_MOVING_SPHERE: // center(time) = center0 + ((time - time0) / (time1 - time0)) * (center1 - center0), moving_sphere.rs:23-26
         type = P_MOVING_SPHERE;
-        const double st0 = p[6], st1 = p[7];
-        double T0 = fp.time0, T1 = fp.time1;
-        if (!(T1 != T0)) T0 = st0, T1 = st1; // degenerate scope: keep the sphere's own interval
-        for (int k = 0; k < 3; ++k) {
-            double ca = p[k] + ((T0 - st0) / (st1 - st0)) * (p[3 + k] - p[k]);
-            double cb = p[k] + ((T1 - st0) / (st1 - st0)) * (p[3 + k] - p[k]);
-            q[k] = float(ca), q[4 + k] = float(cb - ca);
-        }
-        q[3] = float(p[8]), q[7] = float(T0), q[8] = float(1.0 / (T1 - T0));
+        for (int k = 0; k < 3; ++k) d.p[k] = p[k], d.f[k] = float(p[3 + k] - p[k]);
+        d.p[3] = p[8];
+        d.f[3] = float(p[6]), d.f[4] = float(1.0 / (p[7] - p[6]));
         break;
-    }
     case RT1W_NODE_XY_RECT:
     case RT1W_NODE_XZ_RECT:
     case RT1W_NODE_YZ_RECT:
         type = fp.kind == RT1W_NODE_XY_RECT ? P_XY_RECT : (fp.kind == RT1W_NODE_XZ_RECT ? P_XZ_RECT : P_YZ_RECT);
-        for (int i = 0; i < 5; ++i) q[i] = float(p[i]);
+        for (int i = 0; i < 4; ++i) d.p[i] = p[i];
+        d.q[0] = p[4];
         break;
     case RT1W_NODE_CONSTANT_MEDIUM:
-        if (fp.boundary == RT1W_NODE_SPHERE) {
+        if (fp.boundary == RT1W_NODE_SPHERE) { // p = center, radius, -1/density
             type = P_MEDIUM_SPHERE;
-            for (int i = 0; i < 5; ++i) q[i] = float(p[i]);
-        } else {
+            for (int i = 0; i < 4; ++i) d.p[i] = p[i];
+            d.q[0] = p[4];
+        } else { // p = min xyz, -1/density, max xyz
             type = P_MEDIUM_BOX;
-            for (int i = 0; i < 7; ++i) q[i] = float(p[i]);
+            for (int i = 0; i < 4; ++i) d.p[i] = p[i];
+            for (int i = 0; i < 3; ++i) d.q[i] = p[4 + i];
         }
         break;
     default: break;
     }
-    for (int i = 0; i < 4; ++i) d.p03[i] = q[i], d.p69[i] = q[6 + i], d.p1013[i] = q[10 + i];
-    d.p4 = q[4], d.p5 = q[5];
     d.meta = pack_meta(type, fp.flags, materials[fp.material].type, fp.material);
     d.frame = fp.frame;
     return d;

@@ -35,7 +35,7 @@ rt1w_status fail_cuda(const char *what, cudaError_t e) {
     } while (0)
 
 constexpr uint32_t kDefaultPool = 1u << 20;
-constexpr int kMaxLeaf = 2;
+constexpr int kMaxLeaf = 1; // single-primitive leaves: the f32 leaf-box test screens the f64 primitive solve
 
 template <class T> cudaError_t upload(const std::vector<T> &v, T **out) {
     *out = nullptr;
@@ -69,6 +69,7 @@ struct rt1w_scene {
     // device allocations
     float4 *d_nodes = nullptr;
     DPrim *d_prims = nullptr;
+    float4 *d_prim_boxes = nullptr;
     int32_t *d_prim_id = nullptr;
     DFrame *d_frames = nullptr;
     DMaterial *d_materials = nullptr;
@@ -86,7 +87,7 @@ static void scene_release(rt1w_scene *s) {
     if (s->ctx) cudaSetDevice(s->ctx->device);
     for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
     for (auto a : s->arrays) cudaFreeArray(a);
-    cudaFree(s->d_nodes), cudaFree(s->d_prims), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
+    cudaFree(s->d_nodes), cudaFree(s->d_prims), cudaFree(s->d_prim_boxes), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
     cudaFree(s->d_textures), cudaFree(s->d_perlins), cudaFree(s->d_images), cudaFree(s->d_image_dims), cudaFree(s->d_lights);
     delete s;
 }
@@ -168,9 +169,14 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     if (bvh.depth > kStackSmem + kStackLocal - 2) return fail(RT1W_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
     std::vector<DPrim> dprims(n);
     std::vector<int32_t> prim_id(n);
+    std::vector<float4> prim_boxes(2 * n);
     for (size_t i = 0; i < n; ++i) {
-        dprims[i] = make_device_prim(low.prims[bvh.prim_order[i]], low.materials);
+        const rt1w_flat_prim &fp = low.prims[bvh.prim_order[i]];
+        dprims[i] = make_device_prim(fp, low.materials);
         prim_id[i] = int32_t(bvh.prim_order[i]);
+        float lo[3], hi[3];
+        conservative_box(fp.bbox_min, fp.bbox_max, lo, hi);
+        prim_boxes[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.0f), prim_boxes[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
     }
     const auto t1 = std::chrono::steady_clock::now();
 
@@ -181,6 +187,7 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
     RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
     RT1W_CUDA(upload(dprims, &s->d_prims));
+    RT1W_CUDA(upload(prim_boxes, &s->d_prim_boxes));
     RT1W_CUDA(upload(prim_id, &s->d_prim_id));
     RT1W_CUDA(upload(low.frames, &s->d_frames));
     RT1W_CUDA(upload(low.materials, &s->d_materials));
@@ -217,7 +224,7 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     const auto t2 = std::chrono::steady_clock::now();
 
     SceneView &v = s->view;
-    v.nodes = s->d_nodes, v.prims = s->d_prims, v.prim_id = s->d_prim_id, v.frames = s->d_frames;
+    v.nodes = s->d_nodes, v.prims = s->d_prims, v.prim_boxes = s->d_prim_boxes, v.prim_id = s->d_prim_id, v.frames = s->d_frames;
     v.materials = s->d_materials, v.textures = s->d_textures, v.perlins = s->d_perlins;
     v.images = s->d_images, v.image_dims = s->d_image_dims, v.lights = s->d_lights;
     v.n_lights = int32_t(low.lights.size()), v.has_lights = low.has_lights ? 1 : 0;

@@ -37,15 +37,7 @@ struct Builder {
 
     // Conservative f32 bounds: round outward and pad, so that f32 slab arithmetic never culls
     // a primitive the f64 reference would reach.
-    void store_box(BvhNode32 &n, const Box &b) const {
-        for (int k = 0; k < 3; ++k) {
-            double ext = std::max(b.hi[k] - b.lo[k], std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
-            double pad = 1e-5 * ext + 1e-5;
-            float lo = float(b.lo[k] - pad), hi = float(b.hi[k] + pad);
-            n.min[k] = std::nextafter(lo, -std::numeric_limits<float>::infinity());
-            n.max[k] = std::nextafter(hi, std::numeric_limits<float>::infinity());
-        }
-    }
+    void store_box(BvhNode32 &n, const Box &b) const { conservative_box(b.lo, b.hi, n.min, n.max); }
 
     void make_leaf(uint32_t node, uint32_t first, uint32_t count, const Box &b, int depth) {
         store_box(nodes[node], b);
@@ -133,6 +125,16 @@ struct Builder {
 };
 
 } // namespace
+
+void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3]) {
+    for (int k = 0; k < 3; ++k) {
+        double ext = std::max(hi[k] - lo[k], std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+        double pad = 1e-5 * ext + 1e-5;
+        float l = float(lo[k] - pad), h = float(hi[k] + pad);
+        out_min[k] = std::nextafter(l, -std::numeric_limits<float>::infinity());
+        out_max[k] = std::nextafter(h, std::numeric_limits<float>::infinity());
+    }
+}
 
 void build_sah_bvh(const double *bmin, const double *bmax, size_t n, int max_leaf, BvhBuildResult &out) {
     out.nodes.clear();

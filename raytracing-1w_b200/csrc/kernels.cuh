@@ -31,6 +31,7 @@ constexpr int kStackLocal = 40;      // overflow entries (local memory; the buil
 struct SceneView {
     const float4 *nodes;       // 2 x float4 per node
     const DPrim *prims;        // leaf order
+    const float4 *prim_boxes;  // 2 x float4 per primitive (leaf order): its padded f32 bounds
     const int32_t *prim_id;    // leaf index -> primitive id (DFS order of the description)
     const DFrame *frames;
     const DMaterial *materials;
@@ -144,12 +145,14 @@ RT1W_DEV bool hit_sphere(const LocalRay &l, double cx, double cy, double cz, dou
     return true;
 }
 
-// rect with constant axis AX (0: YZRect, 1: XZRect, 2: XYRect); aarect.rs:46-72,84-110,152-178
-template <int AX> RT1W_DEV bool hit_rect(const LocalRay &l, double a0, double a1, double b0, double b1, double k, double tmin, double tmax, double &t) {
-    const double oc = AX == 0 ? l.ox : (AX == 1 ? l.oy : l.oz);
-    const double dc = AX == 0 ? l.dx : (AX == 1 ? l.dy : l.dz);
-    const double oa = AX == 0 ? l.oy : l.ox, da = AX == 0 ? l.dy : l.dx;
-    const double ob = AX == 2 ? l.oy : l.oz, db = AX == 2 ? l.dy : l.dz;
+// rect with constant axis ax (0: YZRect, 1: XZRect, 2: XYRect); aarect.rs:46-72,84-110,152-178.
+// The axis is data, not a template parameter: lanes of a warp that test different rectangles
+// (walls, box sides) run the same instruction stream.
+RT1W_DEV bool hit_rect(const LocalRay &l, int ax, double a0, double a1, double b0, double b1, double k, double tmin, double tmax, double &t) {
+    const double oc = ax == 0 ? l.ox : (ax == 1 ? l.oy : l.oz);
+    const double dc = ax == 0 ? l.dx : (ax == 1 ? l.dy : l.dz);
+    const double oa = ax == 0 ? l.oy : l.ox, da = ax == 0 ? l.dy : l.dx;
+    const double ob = ax == 2 ? l.oy : l.oz, db = ax == 2 ? l.dy : l.dz;
     const double tt = (k - oc) / dc;
     if (tt < tmin || tt > tmax) return false;
     const double a = oa + tt * da, b = ob + tt * db;
@@ -174,35 +177,37 @@ RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, d
     return true;
 }
 
-// One candidate primitive.  Returns true and the hit parameter when it beats (tmin, tmax].
-template <bool EXACT> RT1W_DEV bool hit_prim(const SceneView &sc, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
-    const double2 *w = reinterpret_cast<const double2 *>(sc.prims + leaf);
-    const int4 tail = __ldg(reinterpret_cast<const int4 *>(w + 3)); // q2 | meta | frame
+// One candidate primitive (record at `P`: global memory, or the shared-memory copy of the flat-scan
+// path).  Returns true and the hit parameter when it lands in [t_min, tmax].
+template <bool EXACT>
+RT1W_DEV bool hit_prim(const SceneView &sc, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
+    const double2 *w = reinterpret_cast<const double2 *>(P);
+    const int4 tail = *reinterpret_cast<const int4 *>(w + 3); // q2 | meta | frame
     const uint32_t meta = uint32_t(tail.z);
     const int type = int(meta & 15u);
-    const double2 p01 = __ldg(w), p23 = __ldg(w + 1);
+    const double2 p01 = w[0], p23 = w[1];
     const LocalRay l = to_local(sc, tail.w, r);
     switch (type) {
     case P_SPHERE: return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
     case P_MOVING_SPHERE: { // moving_sphere.rs:23-26,31-48
-        const float4 f = __ldg(reinterpret_cast<const float4 *>(w + 2));
+        const float4 f = *reinterpret_cast<const float4 *>(w + 2);
         const double s = double((r.time - f.w) * __int_as_float(tail.x));
         return hit_sphere(l, p01.x + s * double(f.x), p01.y + s * double(f.y), p23.x + s * double(f.z), p23.y, kTMin, tmax, t);
     }
-    case P_XY_RECT: return hit_rect<2>(l, p01.x, p01.y, p23.x, p23.y, __ldg(reinterpret_cast<const double *>(w + 2)), kTMin, tmax, t);
-    case P_XZ_RECT: return hit_rect<1>(l, p01.x, p01.y, p23.x, p23.y, __ldg(reinterpret_cast<const double *>(w + 2)), kTMin, tmax, t);
-    case P_YZ_RECT: return hit_rect<0>(l, p01.x, p01.y, p23.x, p23.y, __ldg(reinterpret_cast<const double *>(w + 2)), kTMin, tmax, t);
+    case P_XY_RECT:
+    case P_XZ_RECT:
+    case P_YZ_RECT: return hit_rect(l, P_YZ_RECT - type, p01.x, p01.y, p23.x, p23.y, w[2].x, kTMin, tmax, t);
     case P_MEDIUM_SPHERE: { // boundary.hit(-inf, inf) then boundary.hit(t1 + 0.0001, inf), constant_medium.rs:58-72
         double r0, r1;
         if (!sphere_roots(l, p01.x, p01.y, p23.x, p23.y, r0, r1)) return false;
         if (r1 < r0 + 0.0001) return false;
-        const double nid = __ldg(reinterpret_cast<const double *>(w + 2));
+        const double nid = w[2].x;
         const double len = sqrt(l.dx * l.dx + l.dy * l.dy + l.dz * l.dz);
         const uint32_t id = EXACT ? uint32_t(__ldg(sc.prim_id + leaf)) : uint32_t(leaf);
         return medium_sample<EXACT>(r0, r1, nid, len, kTMin, tmax, mr, id, t);
     }
     case P_MEDIUM_BOX: { // the six sides of aabox.rs:29-76 as three slabs
-        const double2 q01 = __ldg(w + 2);
+        const double2 q01 = w[2];
         const double q2 = __hiloint2double(tail.y, tail.x);
         const double ix = 1.0 / l.dx, iy = 1.0 / l.dy, iz = 1.0 / l.dz;
         double ax = (p01.x - l.ox) * ix, bx = (q01.x - l.ox) * ix;
@@ -239,62 +244,121 @@ RT1W_DEV bool slab(const float4 lo, const float4 hi, const SlabRay &s, float tma
     return tn <= tf;
 }
 
-// `stack` points at this thread's column of the shared short stack (stride = blockDim.x).
+// Node references on the traversal stack: primitive count in the top 3 bits, left_first below.
+RT1W_DEV uint32_t node_ref(float4 n0, float4 n1) { return (__float_as_uint(n1.w) << 29) | __float_as_uint(n0.w); }
+
+// `stack` points at this thread's column of the shared short stack (stride = blockDim.x); an entry is
+// (node reference, entry distance) so that subtrees the current best hit already beats are dropped on pop.
+// while-while traversal: every lane descends to its next leaf before any lane runs the (f64) primitive
+// tests, so those run with most of the warp converged.
 template <bool EXACT>
-RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr, uint32_t *stack, int stride, double &t_best, int &leaf_best) {
+RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
     SlabRay s;
     s.ox = float(r.ox), s.oy = float(r.oy), s.oz = float(r.oz);
     s.ix = 1.0f / r.dx, s.iy = 1.0f / r.dy, s.iz = 1.0f / r.dz;
     double best = CUDART_INF;
     float bestf = CUDART_INF_F;
     int best_leaf = -1;
-    uint32_t overflow[kStackLocal];
+    uint2 overflow[kStackLocal];
     int sp = 0;
-    uint32_t node = 0;
+    uint32_t ref;
     {
+        const float4 n0 = __ldg(sc.nodes), n1 = __ldg(sc.nodes + 1);
         float tn;
-        if (!slab(__ldg(sc.nodes), __ldg(sc.nodes + 1), s, bestf, tn)) {
+        if (!slab(n0, n1, s, bestf, tn)) {
             t_best = best, leaf_best = -1;
             return false;
         }
+        ref = node_ref(n0, n1);
     }
-    for (;;) {
-        const float4 n0 = __ldg(sc.nodes + 2 * node), n1 = __ldg(sc.nodes + 2 * node + 1);
-        const uint32_t left_first = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
-        bool pop = true;
-        if (count == 0) {
-            const float4 *c = sc.nodes + 2 * left_first;
+    auto pop = [&]() -> bool { // next stacked subtree that can still contain a closer hit
+        while (sp > 0) {
+            --sp;
+            const uint2 e = sp < kStackSmem ? stack[sp * stride] : overflow[sp - kStackSmem];
+            if (__uint_as_float(e.y) <= bestf) {
+                ref = e.x;
+                return true;
+            }
+        }
+        return false;
+    };
+    bool alive = true;
+    while (alive) {
+        while ((ref >> 29) == 0u) { // interior: children at ref, ref + 1 (one 64-byte pair)
+            const float4 *c = sc.nodes + 2 * ref;
             const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
             float tl, tr;
             const bool hl = slab(l0, l1, s, bestf, tl), hr = slab(r0, r1, s, bestf, tr);
+            const uint32_t refl = node_ref(l0, l1), refr = node_ref(r0, r1);
             if (hl && hr) {
-                const bool left_first_order = tl <= tr;
-                const uint32_t near_n = left_first_order ? left_first : left_first + 1;
-                const uint32_t far_n = left_first_order ? left_first + 1 : left_first;
-                if (sp < kStackSmem) stack[sp * stride] = far_n;
-                else overflow[sp - kStackSmem] = far_n;
+                const bool left_near = tl <= tr;
+                const uint2 far_e = make_uint2(left_near ? refr : refl, __float_as_uint(left_near ? tr : tl));
+                if (sp < kStackSmem) stack[sp * stride] = far_e;
+                else overflow[sp - kStackSmem] = far_e;
                 ++sp;
-                node = near_n;
-                pop = false;
+                ref = left_near ? refl : refr;
             } else if (hl || hr) {
-                node = hl ? left_first : left_first + 1;
-                pop = false;
-            }
-        } else {
-            for (uint32_t i = 0; i < count; ++i) {
-                double t;
-                if (hit_prim<EXACT>(sc, int(left_first + i), r, best, mr, t)) {
-                    best = t, best_leaf = int(left_first + i);
-                    bestf = __double2float_ru(t);
-                }
+                ref = hl ? refl : refr;
+            } else if (!pop()) {
+                alive = false;
+                break;
             }
         }
-        if (pop) {
-            // skip stacked subtrees that the current best already culls is left to the slab test on pop
-            if (sp == 0) break;
-            --sp;
-            node = sp < kStackSmem ? stack[sp * stride] : overflow[sp - kStackSmem];
+        if (!alive) break;
+        const uint32_t first = ref & 0x1fffffffu, count = ref >> 29;
+        for (uint32_t i = 0; i < count; ++i) {
+            double t;
+            if (hit_prim<EXACT>(sc, sc.prims + (first + i), int(first + i), r, best, mr, t)) {
+                best = t, best_leaf = int(first + i);
+                bestf = __double2float_ru(t);
+            }
         }
+        alive = pop();
+    }
+    t_best = best, leaf_best = best_leaf;
+    return best_leaf >= 0;
+}
+
+// Small scenes (<= kFlatMax primitives, e.g. the 13 of the Cornell box): a BVH over a handful of
+// room-sized rectangles culls nothing, so the extend kernel scans the primitive list instead.  The
+// records and their padded f32 boxes sit in shared memory, every lane walks the same primitive at the
+// same time (broadcast reads, no traversal divergence) and the f32 box test screens the f64 solve.
+constexpr int kFlatMax = 32;
+
+struct FlatScene {
+    DPrim prims[kFlatMax];
+    float4 lo[kFlatMax], hi[kFlatMax];
+};
+
+RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the whole CTA, then __syncthreads()
+    const int n = sc.n_prims;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(sc.prims);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(fs.prims);
+    for (int w = threadIdx.x; w < n * int(sizeof(DPrim) / 4); w += blockDim.x) dst[w] = src[w];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) fs.lo[i] = sc.prim_boxes[2 * i], fs.hi[i] = sc.prim_boxes[2 * i + 1];
+}
+
+template <bool EXACT>
+RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const Ray &r, const MediumRng &mr, double &t_best, int &leaf_best) {
+    SlabRay s;
+    s.ox = float(r.ox), s.oy = float(r.oy), s.oz = float(r.oz);
+    s.ix = 1.0f / r.dx, s.iy = 1.0f / r.dy, s.iz = 1.0f / r.dz;
+    double best = CUDART_INF;
+    float bestf = CUDART_INF_F;
+    int best_leaf = -1;
+    const int n = sc.n_prims;
+    // pass 1 (warp-uniform): which primitive boxes does this ray cross?
+    uint32_t cand = 0;
+    for (int i = 0; i < n; ++i) {
+        float tn;
+        if (slab(fs.lo[i], fs.hi[i], s, bestf, tn)) cand |= 1u << i;
+    }
+    // pass 2: every lane walks its own candidates; lanes testing different rectangles share one code path
+    while (cand) {
+        const int i = __ffs(int(cand)) - 1;
+        cand &= cand - 1u;
+        double t;
+        if (hit_prim<EXACT>(sc, fs.prims + i, i, r, best, mr, t)) best = t, best_leaf = i;
     }
     t_best = best, leaf_best = best_leaf;
     return best_leaf >= 0;

@@ -20,7 +20,6 @@ namespace rt1w {
 constexpr int kGenThreads = 256;
 constexpr int kExtendThreads = 128;
 constexpr int kShadeThreads = 128;
-constexpr int kFreeQueue = Q_COUNT; // destination code for "slot terminated"
 
 // ------------------------------------------------------------------------------------------
 // Queue push: one atomic per warp per queue.
@@ -34,6 +33,26 @@ RT1W_DEV void warp_push(uint32_t *__restrict__ queue, uint32_t *counter, bool pr
     if (lane == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pred) queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// Sorts the lanes of a warp into the queues of the table with ONE atomic instruction: lane q reserves
+// queue q's slots for the whole warp (QS_COUNT lanes, QS_COUNT addresses, one round trip), then every
+// lane fetches the base of its own destination with a shuffle.  dest < 0: the lane pushes nothing.
+// `live` is a compile-time mask of the queue slots this call site can produce.
+template <uint32_t LIVE> RT1W_DEV void warp_sort_push(const Pool &pool, int dest, uint32_t value) {
+    const int lane = threadIdx.x & 31;
+    uint32_t mine = 0, count_for_lane = 0;
+#pragma unroll
+    for (int q = 0; q < QS_COUNT; ++q) {
+        if (!(LIVE & (1u << q))) continue;
+        const unsigned m = __ballot_sync(0xffffffffu, dest == q);
+        if (dest == q) mine = m;
+        if (lane == q) count_for_lane = uint32_t(__popc(m));
+    }
+    uint32_t base = 0;
+    if (count_for_lane) base = atomicAdd(&pool.ctr->n[lane], count_for_lane);
+    base = __shfl_sync(0xffffffffu, base, dest < 0 ? 0 : dest);
+    if (dest >= 0) pool.q[dest][base + __popc(mine & ((1u << lane) - 1u))] = value;
 }
 
 // A path ends: pixel += throughput * radiance.  A NaN product must reach the sum even when the
@@ -94,14 +113,14 @@ RT1W_DEV uint32_t purpose_word(const DRenderParams &rp, uint32_t stream) { retur
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant__ RenderArgs a, const int parity, const int initial) {
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = initial ? a.pool.capacity : ctr->n_free[parity ^ 1];
+    const uint32_t n = initial ? a.pool.capacity : ctr->n[QS_FREE + (parity ^ 1)];
     if (blockIdx.x == 0 && threadIdx.x == 0) { // recycle the counters nobody reads during this wave's generate
 #pragma unroll
-        for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[q] = 0;
-        ctr->n_free[parity] = 0;
-        ctr->n_extend[parity ^ 1] = 0;
+        for (int q = 0; q < Q_COUNT; ++q) ctr->n[QS_MAT + q] = 0;
+        ctr->n[QS_FREE + parity] = 0;
+        ctr->n[QS_EXTEND + (parity ^ 1)] = 0;
     }
-    const uint32_t *free_q = a.pool.q_free[parity ^ 1];
+    const uint32_t *free_q = a.pool.q[QS_FREE + (parity ^ 1)];
     const unsigned long long total = a.rp.total_paths;
     const int lane = threadIdx.x & 31;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
@@ -149,20 +168,32 @@ __global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant_
             store_ray(a.pool, slot, a.cam.origin[0] + offx, a.cam.origin[1] + offy, a.cam.origin[2] + offz, d, time, sample_rel << 8, pixel);
             a.pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         }
-        warp_push(a.pool.q_extend[parity], &ctr->n_extend[parity], live, slot);
+        warp_push(a.pool.q[QS_EXTEND + parity], &ctr->n[QS_EXTEND + parity], live, slot);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // extend
 // ------------------------------------------------------------------------------------------
+// FLAT: scan the primitive list staged in shared memory (scenes of <= kFlatMax primitives) instead of walking the BVH.
+template <bool FLAT>
 __global__ void __launch_bounds__(kExtendThreads) k_extend(const __grid_constant__ RenderArgs a, const int parity, const int material_mask) {
-    __shared__ uint32_t s_stack[kStackSmem * kExtendThreads];
+    // one shared buffer: the staged primitive list (FLAT) or the per-thread traversal stacks (BVH)
+    __shared__ __align__(16) unsigned char s_raw[FLAT ? sizeof(FlatScene) : sizeof(uint2) * kStackSmem * kExtendThreads];
+    uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
+    FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = ctr->n_extend[parity];
+    const uint32_t n = ctr->n[QS_EXTEND + parity];
+    if (n == 0) return;
+    if (FLAT) {
+        flat_stage(a.sc, s_flat[0]);
+        __syncthreads();
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->rays, (unsigned long long)n);
-    const uint32_t *in_q = a.pool.q_extend[parity];
+    const uint32_t *in_q = a.pool.q[QS_EXTEND + parity];
     const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
+    const bool has_media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
+    const int free_dest = QS_FREE + parity;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         const bool valid = i < n;
@@ -172,17 +203,20 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(const __grid_constant
             slot = in_q[i];
             RayC c;
             const Ray r = load_ray(a.pool, slot, c);
-            MediumRng mr;
-            path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
-            mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
+            MediumRng mr = {0, 0, 0, 0, 0};
+            if (has_media) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
+                path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
+                mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
+            }
             double t;
             int leaf;
-            const bool hit = closest_hit<false>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
+            const bool hit = FLAT ? closest_hit_flat<false>(a.sc, s_flat[0], r, mr, t, leaf)
+                                  : closest_hit<false>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
             if (hit) {
-                const uint32_t meta = __ldg(&a.sc.prims[leaf].meta);
+                const uint32_t meta = FLAT ? s_flat[0].prims[leaf].meta : __ldg(&a.sc.prims[leaf].meta);
                 const int mat_type = int((meta >> 8) & 15u);
                 if (mat_type == RT1W_MAT_NONE) { // `impl Material for ()`: no emission, no scatter (material.rs:68)
-                    dest = kFreeQueue;
+                    dest = free_dest;
                 } else {
                     HitRec h;
                     h.t = t, h.leaf = leaf, h.pad = 0;
@@ -190,20 +224,17 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(const __grid_constant
                     dest = mat_type;
                 }
             } else {
-                dest = kFreeQueue;
+                dest = free_dest;
             }
-            if (dest == kFreeQueue) { // main.rs:113-115 (miss -> background) or a null-material hit (zero radiance)
+            if (dest == free_dest) { // main.rs:113-115 (miss -> background) or a null-material hit (zero radiance)
                 const float4 th = a.pool.thr[slot];
                 const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
-                if (has_background || !(th.x == th.x) || !(th.y == th.y) || !(th.z == th.z) || isinf(th.x) || isinf(th.y) || isinf(th.z))
-                    splat(a, c.pixel, mk3(th.x, th.y, th.z), rad);
+                const bool finite = (fabsf(th.x) + fabsf(th.y) + fabsf(th.z)) < CUDART_INF_F; // false for NaN and inf
+                if (has_background || !finite) splat(a, c.pixel, mk3(th.x, th.y, th.z), rad);
             }
         }
         __syncwarp();
-#pragma unroll
-        for (int q = 0; q < Q_COUNT; ++q)
-            if (material_mask & (1 << q)) warp_push(a.pool.q_mat[q], &ctr->n_mat[q], dest == q, slot);
-        warp_push(a.pool.q_free[parity], &ctr->n_free[parity], dest == kFreeQueue, slot);
+        warp_sort_push<(1u << (Q_COUNT + 2)) - 1u>(a.pool, dest, slot);
     }
 }
 
@@ -214,7 +245,7 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ DLight s_lights[MAT == RT1W_MAT_LAMBERTIAN ? RT1W_MAX_LIGHTS : 1];
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = ctr->n_mat[MAT];
+    const uint32_t n = ctr->n[QS_MAT + MAT];
     if (n == 0) return;
     // stage the Perlin tables (perlin.rs:7-12) and the light list in shared memory
     const DPerlin *perlins = a.sc.perlins;
@@ -231,7 +262,7 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
     }
     __syncthreads();
 
-    const uint32_t *in_q = a.pool.q_mat[MAT];
+    const uint32_t *in_q = a.pool.q[QS_MAT + MAT];
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         const bool valid = i < n;
@@ -273,8 +304,8 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
                     dir = random_in_unit_sphere(rng);
                 }
                 if (depth + 1u >= uint32_t(a.rp.max_depth)) { // main.rs:59-61: the next ray_color call returns black
-                    const bool bad = !(thr.x == thr.x) || !(thr.y == thr.y) || !(thr.z == thr.z) || isinf(thr.x) || isinf(thr.y) || isinf(thr.z);
-                    if (bad) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
+                    const bool finite = (fabsf(thr.x) + fabsf(thr.y) + fabsf(thr.z)) < CUDART_INF_F; // false for NaN and inf
+                    if (!finite) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
                     ended = true;
                 } else {
                     store_ray(a.pool, slot, h.px, h.py, h.pz, dir, time, c.state + 1u, c.pixel);
@@ -284,8 +315,8 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
             }
         }
         __syncwarp();
-        if (MAT != RT1W_MAT_DIFFUSE_LIGHT) warp_push(a.pool.q_extend[parity ^ 1], &ctr->n_extend[parity ^ 1], go_on, slot);
-        warp_push(a.pool.q_free[parity], &ctr->n_free[parity], ended, slot);
+        warp_sort_push<((1u << QS_FREE) | (1u << (QS_FREE + 1)) | (1u << QS_EXTEND) | (1u << (QS_EXTEND + 1)))>(
+            a.pool, go_on ? QS_EXTEND + (parity ^ 1) : (ended ? QS_FREE + parity : -1), slot);
     }
 }
 
@@ -295,7 +326,13 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
 __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant__ SceneView sc, const rt1w_ray *__restrict__ rays, const size_t n,
                                                           const uint32_t seed_lo, const uint32_t seed_hi, int32_t *prim_id, float *t_out,
                                                           float *normal3, uint8_t *front_face, float *uv2) {
-    __shared__ uint32_t s_stack[kStackSmem * kExtendThreads];
+    __shared__ uint2 s_stack[kStackSmem * kExtendThreads];
+    __shared__ FlatScene s_flat;
+    const bool flat = sc.n_prims <= kFlatMax; // same choice as the render path, so parity covers both traversals
+    if (flat) {
+        flat_stage(sc, s_flat);
+        __syncthreads();
+    }
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         const rt1w_ray in = rays[i];
         Ray r;
@@ -306,7 +343,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
         mr.c0 = uint32_t(i), mr.c1 = uint32_t(uint64_t(i) >> 32), mr.c2 = RNG_TRACE_MEDIUM, mr.k0 = seed_lo, mr.k1 = seed_hi;
         double t;
         int leaf;
-        const bool hit = closest_hit<true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
+        const bool hit = flat ? closest_hit_flat<true>(sc, s_flat, r, mr, t, leaf) : closest_hit<true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
         HitInfo h;
         if (hit) h = finalize_hit<true>(sc, leaf, r, t);
         if (prim_id) prim_id[i] = hit ? sc.prim_id[leaf] : -1;
@@ -335,11 +372,7 @@ cudaError_t pool_alloc(Pool &pool, uint32_t capacity) {
     RT1W_TRY(cudaMalloc(&pool.dzm, sizeof(RayC) * size_t(capacity)));
     RT1W_TRY(cudaMalloc(&pool.thr, sizeof(float4) * size_t(capacity)));
     RT1W_TRY(cudaMalloc(&pool.hit, sizeof(HitRec) * size_t(capacity)));
-    for (int k = 0; k < 2; ++k) {
-        RT1W_TRY(cudaMalloc(&pool.q_extend[k], sizeof(uint32_t) * size_t(capacity)));
-        RT1W_TRY(cudaMalloc(&pool.q_free[k], sizeof(uint32_t) * size_t(capacity)));
-    }
-    for (int q = 0; q < Q_COUNT; ++q) RT1W_TRY(cudaMalloc(&pool.q_mat[q], sizeof(uint32_t) * size_t(capacity)));
+    for (int q = 0; q < QS_COUNT; ++q) RT1W_TRY(cudaMalloc(&pool.q[q], sizeof(uint32_t) * size_t(capacity)));
     RT1W_TRY(cudaMalloc(&pool.ctr, sizeof(Counters)));
 #undef RT1W_TRY
     pool.capacity = capacity;
@@ -348,8 +381,7 @@ cudaError_t pool_alloc(Pool &pool, uint32_t capacity) {
 
 void pool_free(Pool &pool) {
     cudaFree(pool.o_xy), cudaFree(pool.o_zd), cudaFree(pool.dzm), cudaFree(pool.thr), cudaFree(pool.hit);
-    for (int k = 0; k < 2; ++k) cudaFree(pool.q_extend[k]), cudaFree(pool.q_free[k]);
-    for (int q = 0; q < Q_COUNT; ++q) cudaFree(pool.q_mat[q]);
+    for (int q = 0; q < QS_COUNT; ++q) cudaFree(pool.q[q]);
     cudaFree(pool.ctr);
     pool = Pool();
 }
@@ -371,6 +403,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     const int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
     if (!perlin_in_smem) perlin_bytes = 0;
     const int poll_every = 8;
+    const bool flat = args.sc.n_prims <= kFlatMax;
 
     // profiling mode: one event before every launch and one at the end of the chunk
     struct Mark {
@@ -405,7 +438,8 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
             mark(K_GENERATE);
             k_generate<<<gen_blocks, kGenThreads, 0, stream>>>(args, parity, wave == 0 ? 1 : 0);
             mark(K_EXTEND);
-            k_extend<<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
+            if (flat) k_extend<true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
+            else k_extend<false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
             ws.launches += 2;
 #define RT1W_SHADE(MAT, SMEM, PSM)                                                                                                                    \
     if (material_mask & (1 << MAT)) {                                                                                                                 \
@@ -426,7 +460,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) break;
         drain_marks();
         // after wave (wave-1): continuing paths sit in q_extend[wave & 1]
-        if (h_ctr->next_path >= args.rp.total_paths && h_ctr->n_extend[wave & 1] == 0) break;
+        if (h_ctr->next_path >= args.rp.total_paths && h_ctr->n[QS_EXTEND + (wave & 1)] == 0) break;
     }
     for (auto &m : marks) cudaEventDestroy(m.ev);
     for (auto ev : spare) cudaEventDestroy(ev);

@@ -11,11 +11,18 @@
 namespace rt1w {
 
 // Device-side counters of the wavefront queues (one struct per context, zeroed per render).
+// Queue table: one index space for every queue so that a lane can address "its" queue with a
+// register index into kernel-parameter (constant-bank) arrays.
+enum QueueSlot : int {
+    QS_MAT = 0,             // + rt1w_material_type: hits queued for the shade kernels of the current wave
+    QS_FREE = Q_COUNT,      // + (wave & 1): path slots that terminated during wave w
+    QS_EXTEND = Q_COUNT + 2, // + (wave & 1): rays queued for the extend kernel of wave w
+    QS_COUNT = Q_COUNT + 4
+};
+
 struct Counters {
-    uint32_t n_extend[2];     // rays queued for the extend kernel of wave w (index w & 1)
-    uint32_t n_free[2];       // path slots that terminated during wave w (index w & 1)
-    uint32_t n_mat[Q_COUNT];  // hits queued per material family for the shade kernels of the current wave
-    uint32_t pad;
+    uint32_t n[QS_COUNT];         // entries per queue
+    uint32_t pad[3];
     unsigned long long next_path; // next (pixel, sample) pair to start
     unsigned long long rays;      // closest-hit queries so far
 };
@@ -27,9 +34,7 @@ struct Pool {
     RayC *dzm = nullptr;     // direction.z, time, state, pixel
     float4 *thr = nullptr;   // throughput rgb (+ unused lane)
     HitRec *hit = nullptr;   // t, leaf
-    uint32_t *q_extend[2] = {nullptr, nullptr};
-    uint32_t *q_free[2] = {nullptr, nullptr};
-    uint32_t *q_mat[Q_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t *q[QS_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // slot-index queues (QueueSlot)
     Counters *ctr = nullptr;
     uint32_t capacity = 0;
 };

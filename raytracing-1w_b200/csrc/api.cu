@@ -266,8 +266,8 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     if (p.max_depth < 0 || p.max_depth > 255) return fail(RT1W_ERR_UNSUPPORTED, "max_depth must be in [0, 255]");
     if (uint64_t(p.width) * uint64_t(p.height) >= (1ull << 31)) return fail(RT1W_ERR_UNSUPPORTED, "image too large");
     const uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
-    if (ctx->pool.capacity != want_pool) {
-        cudaError_t e = pool_alloc(ctx->pool, want_pool);
+    if (ctx->pool.capacity != want_pool || (ctx->pool.material_mask & scene->material_mask) != scene->material_mask) {
+        cudaError_t e = pool_alloc(ctx->pool, want_pool, scene->material_mask | ctx->pool.material_mask);
         if (e != cudaSuccess) return fail_cuda("path pool allocation", e);
     }
     RenderArgs args;

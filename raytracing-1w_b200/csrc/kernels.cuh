@@ -80,8 +80,8 @@ struct __align__(16) RayC { // third word: rest of the ray + the path bookkeepin
 };
 struct __align__(16) HitRec {
     double t;
-    int32_t leaf; // index into SceneView::prims (leaf order)
-    uint32_t pad;
+    int32_t leaf;  // index into SceneView::prims (leaf order)
+    uint32_t meta; // the primitive's meta word (material id / type), so shading need not wait for the primitive record
 };
 
 // How ConstantMedium candidates draw their free-flight number (constant_medium.rs:85).

@@ -2,14 +2,16 @@
 //
 // The reference's pixel loop + recursive ray_color (main.rs:51-190, 957-1001) become, per wave:
 //
-//   generate   refills terminated path slots with new camera paths   (main.rs:968-971, camera.rs:61-73)
-//   extend     closest hit over the flat SAH BVH, sorts hits into per-material queues (bvh.rs:25-50 ...)
-//   shade_<m>  one kernel per material family: scatter + pdf weighting (material.rs, pdf.rs)
+//   generate   tops the extend queue up with new camera paths            (main.rs:968-971, camera.rs:61-73)
+//   extend     closest hit per ray, compacts the hits into one queue per material family (bvh.rs:25-50 ...)
+//   shade_<m>  one kernel per material family: scatter + pdf weighting, compacts the surviving rays into
+//              the next wave's extend queue                               (material.rs, pdf.rs)
 //
-// Path state lives in SoA arrays in HBM (render.h: Pool); kernels exchange 4-byte slot indices
-// through queues filled with warp-aggregated atomics (__ballot_sync + __popc + __shfl_sync).
-// The recursion `emitted + attenuation * f * L / pdf` is unrolled into a running throughput:
-// only terminal events (DiffuseLight, miss) carry radiance, so a path adds to its pixel exactly once.
+// Ray and path state live in SoA queues in HBM (render.h: RayQueue).  Rays do not own a slot: every
+// stage reads its input queue front to back (fully coalesced 16-byte-per-lane loads) and appends its
+// survivors to the output queue, compacted with __ballot_sync + __popc + __shfl_sync and one atomic
+// per warp per queue.  The recursion `emitted + attenuation * f * L / pdf` is unrolled into a running
+// throughput: only terminal events (DiffuseLight, miss) carry radiance, so a path adds to its pixel once.
 #include "render.h"
 
 #include <cstdio>
@@ -22,37 +24,35 @@ constexpr int kExtendThreads = 128;
 constexpr int kShadeThreads = 128;
 
 // ------------------------------------------------------------------------------------------
-// Queue push: one atomic per warp per queue.
+// Queue append: the lanes of a warp that hold `pred` get consecutive entries; one atomic per warp.
 // ------------------------------------------------------------------------------------------
-RT1W_DEV void warp_push(uint32_t *__restrict__ queue, uint32_t *counter, bool pred, uint32_t value) {
+RT1W_DEV uint32_t warp_reserve(uint32_t *counter, bool pred) {
     const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0) return;
+    if (m == 0) return 0;
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+    return base + __popc(m & ((1u << lane) - 1u));
 }
 
-// Sorts the lanes of a warp into the queues of the table with ONE atomic instruction: lane q reserves
-// queue q's slots for the whole warp (QS_COUNT lanes, QS_COUNT addresses, one round trip), then every
-// lane fetches the base of its own destination with a shuffle.  dest < 0: the lane pushes nothing.
-// `live` is a compile-time mask of the queue slots this call site can produce.
-template <uint32_t LIVE> RT1W_DEV void warp_sort_push(const Pool &pool, int dest, uint32_t value) {
+// Sorts the lanes of a warp into the per-material hit queues with ONE atomic instruction: lane q
+// reserves queue q's entries for the whole warp (Q_COUNT lanes, Q_COUNT addresses, one round trip),
+// then every lane fetches the base of its own destination with a shuffle.  dest < 0: nothing to append.
+RT1W_DEV uint32_t warp_sort_reserve(Counters *ctr, int dest) {
     const int lane = threadIdx.x & 31;
     uint32_t mine = 0, count_for_lane = 0;
 #pragma unroll
-    for (int q = 0; q < QS_COUNT; ++q) {
-        if (!(LIVE & (1u << q))) continue;
+    for (int q = 0; q < Q_COUNT; ++q) {
         const unsigned m = __ballot_sync(0xffffffffu, dest == q);
         if (dest == q) mine = m;
         if (lane == q) count_for_lane = uint32_t(__popc(m));
     }
     uint32_t base = 0;
-    if (count_for_lane) base = atomicAdd(&pool.ctr->n[lane], count_for_lane);
+    if (count_for_lane) base = atomicAdd(&ctr->n_mat[lane], count_for_lane);
     base = __shfl_sync(0xffffffffu, base, dest < 0 ? 0 : dest);
-    if (dest >= 0) pool.q[dest][base + __popc(mine & ((1u << lane) - 1u))] = value;
+    return base + __popc(mine & ((1u << lane) - 1u));
 }
 
 // A path ends: pixel += throughput * radiance.  A NaN product must reach the sum even when the
@@ -78,10 +78,10 @@ RT1W_DEV void splat(const RenderArgs &a, uint32_t pixel, f3 thr, f3 radiance) {
     }
 }
 
-RT1W_DEV Ray load_ray(const Pool &p, uint32_t slot, RayC &c) {
-    const double2 a = p.o_xy[slot];
-    const RayB b = p.o_zd[slot];
-    c = p.dzm[slot];
+RT1W_DEV Ray load_ray(const RayQueue &q, uint32_t i, RayC &c) {
+    const double2 a = q.a[i];
+    const RayB b = q.b[i];
+    c = q.c[i];
     Ray r;
     r.ox = a.x, r.oy = a.y, r.oz = b.oz;
     r.dx = b.dx, r.dy = b.dy, r.dz = c.dz;
@@ -89,14 +89,14 @@ RT1W_DEV Ray load_ray(const Pool &p, uint32_t slot, RayC &c) {
     return r;
 }
 
-RT1W_DEV void store_ray(const Pool &p, uint32_t slot, double ox, double oy, double oz, f3 d, float time, uint32_t state, uint32_t pixel) {
-    p.o_xy[slot] = make_double2(ox, oy);
+RT1W_DEV void store_ray(const RayQueue &q, uint32_t i, double ox, double oy, double oz, f3 d, float time, uint32_t state, uint32_t pixel) {
+    q.a[i] = make_double2(ox, oy);
     RayB b;
     b.oz = oz, b.dx = d.x, b.dy = d.y;
-    p.o_zd[slot] = b;
+    q.b[i] = b;
     RayC c;
     c.dz = d.z, c.time = time, c.state = state, c.pixel = pixel;
-    p.dzm[slot] = c;
+    q.c[i] = c;
 }
 
 // Philox key/counter of a path: key = (reference pixel seed j*w+i (main.rs:964), seed), counter = (sample, bounce, purpose, block)
@@ -108,67 +108,64 @@ RT1W_DEV void path_rng_key(const DRenderParams &rp, uint32_t pixel, uint32_t &k0
 }
 RT1W_DEV uint32_t purpose_word(const DRenderParams &rp, uint32_t stream) { return stream ^ (rp.seed_hi << 4); }
 
+// Rays of wave w: what the shade kernels of wave w-1 appended plus what generate(w) adds on top.
+RT1W_DEV uint32_t wave_new_paths(const RenderArgs &a, int parity) {
+    const Counters *ctr = a.pool.ctr;
+    const unsigned long long left = a.rp.total_paths - min(a.rp.total_paths, ctr->next_path[parity]);
+    const uint32_t room = a.pool.capacity - ctr->n_ext[parity];
+    return uint32_t(min((unsigned long long)room, left));
+}
+
 // ------------------------------------------------------------------------------------------
 // generate
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant__ RenderArgs a, const int parity, const int initial) {
+__global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant__ RenderArgs a, const int parity) {
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = initial ? a.pool.capacity : ctr->n[QS_FREE + (parity ^ 1)];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { // recycle the counters nobody reads during this wave's generate
+    const uint32_t first = ctr->n_ext[parity];
+    const unsigned long long path0 = ctr->next_path[parity];
+    const uint32_t n = wave_new_paths(a, parity);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // hand the counters of the next wave over; nobody else touches them now
 #pragma unroll
-        for (int q = 0; q < Q_COUNT; ++q) ctr->n[QS_MAT + q] = 0;
-        ctr->n[QS_FREE + parity] = 0;
-        ctr->n[QS_EXTEND + (parity ^ 1)] = 0;
+        for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[q] = 0;
+        ctr->n_ext[parity ^ 1] = 0;
+        ctr->next_path[parity ^ 1] = path0 + n;
     }
-    const uint32_t *free_q = a.pool.q[QS_FREE + (parity ^ 1)];
-    const unsigned long long total = a.rp.total_paths;
-    const int lane = threadIdx.x & 31;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + threadIdx.x;
-        const bool valid = i < n;
-        const uint32_t slot = valid ? (initial ? i : free_q[i]) : 0u;
-        // claim path indices, one atomic per warp
-        const unsigned m = __ballot_sync(0xffffffffu, valid);
-        unsigned long long base = 0;
-        if (lane == 0 && m) base = atomicAdd(&ctr->next_path, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
-        const bool live = valid && k < total;
-        if (live) {
-            const uint32_t sample_rel = uint32_t(k / a.rp.n_pixels);
-            const uint32_t pixel = uint32_t(k - (unsigned long long)sample_rel * a.rp.n_pixels);
-            const uint32_t row = pixel / uint32_t(a.rp.width), col = pixel - row * uint32_t(a.rp.width);
-            const uint32_t j = uint32_t(a.rp.height) - 1u - row; // main.rs:959: rows are emitted top first
-            Rng rng;
-            path_rng_key(a.rp, pixel, rng.k0, rng.k1);
-            rng.c0 = uint32_t(a.rp.sample_begin) + sample_rel, rng.c1 = 0, rng.c2 = purpose_word(a.rp, RNG_CAMERA), rng.block = 0;
-            const Philox4 x = rng.next4();
-            const double s = (double(col) + double(u01(x.x))) / double(a.rp.width - 1);  // main.rs:968
-            const double t = (double(j) + double(u01(x.y))) / double(a.rp.height - 1);   // main.rs:969
-            const float time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01(x.z);     // camera.rs:71
-            double offx = 0.0, offy = 0.0, offz = 0.0;
-            if (a.cam.lens_radius != 0.0) { // camera.rs:62-63; the rejection loop of math.rs:30-37
-                float px, py;
-                for (;;) {
-                    const Philox4 y = rng.next4();
-                    px = 2.0f * u01(y.x) - 1.0f, py = 2.0f * u01(y.y) - 1.0f;
-                    if (px * px + py * py < 1.0f) break;
-                    px = 2.0f * u01(y.z) - 1.0f, py = 2.0f * u01(y.w) - 1.0f;
-                    if (px * px + py * py < 1.0f) break;
-                }
-                const double rx = a.cam.lens_radius * double(px), ry = a.cam.lens_radius * double(py);
-                offx = a.cam.u[0] * rx + a.cam.v[0] * ry;
-                offy = a.cam.u[1] * rx + a.cam.v[1] * ry;
-                offz = a.cam.u[2] * rx + a.cam.v[2] * ry;
+    const RayQueue &out = a.pool.ext[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = path0 + i;
+        const uint32_t sample_rel = uint32_t(k / a.rp.n_pixels);
+        const uint32_t pixel = uint32_t(k - (unsigned long long)sample_rel * a.rp.n_pixels);
+        const uint32_t row = pixel / uint32_t(a.rp.width), col = pixel - row * uint32_t(a.rp.width);
+        const uint32_t j = uint32_t(a.rp.height) - 1u - row; // main.rs:959: rows are emitted top first
+        Rng rng;
+        path_rng_key(a.rp, pixel, rng.k0, rng.k1);
+        rng.c0 = uint32_t(a.rp.sample_begin) + sample_rel, rng.c1 = 0, rng.c2 = purpose_word(a.rp, RNG_CAMERA), rng.block = 0;
+        const Philox4 x = rng.next4();
+        const double s = (double(col) + double(u01(x.x))) / double(a.rp.width - 1);  // main.rs:968
+        const double t = (double(j) + double(u01(x.y))) / double(a.rp.height - 1);   // main.rs:969
+        const float time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01(x.z);     // camera.rs:71
+        double offx = 0.0, offy = 0.0, offz = 0.0;
+        if (a.cam.lens_radius != 0.0) { // camera.rs:62-63; the rejection loop of math.rs:30-37
+            float px, py;
+            for (;;) {
+                const Philox4 y = rng.next4();
+                px = 2.0f * u01(y.x) - 1.0f, py = 2.0f * u01(y.y) - 1.0f;
+                if (px * px + py * py < 1.0f) break;
+                px = 2.0f * u01(y.z) - 1.0f, py = 2.0f * u01(y.w) - 1.0f;
+                if (px * px + py * py < 1.0f) break;
             }
-            // camera.rs:67-70: direction = lower_left_corner + s*horizontal + t*vertical - origin - offset (never normalised)
-            const f3 d = mk3(float(a.cam.llc_rel[0] + s * a.cam.horizontal[0] + t * a.cam.vertical[0] - offx),
-                             float(a.cam.llc_rel[1] + s * a.cam.horizontal[1] + t * a.cam.vertical[1] - offy),
-                             float(a.cam.llc_rel[2] + s * a.cam.horizontal[2] + t * a.cam.vertical[2] - offz));
-            store_ray(a.pool, slot, a.cam.origin[0] + offx, a.cam.origin[1] + offy, a.cam.origin[2] + offz, d, time, sample_rel << 8, pixel);
-            a.pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            const double rx = a.cam.lens_radius * double(px), ry = a.cam.lens_radius * double(py);
+            offx = a.cam.u[0] * rx + a.cam.v[0] * ry;
+            offy = a.cam.u[1] * rx + a.cam.v[1] * ry;
+            offz = a.cam.u[2] * rx + a.cam.v[2] * ry;
         }
-        warp_push(a.pool.q[QS_EXTEND + parity], &ctr->n[QS_EXTEND + parity], live, slot);
+        // camera.rs:67-70: direction = lower_left_corner + s*horizontal + t*vertical - origin - offset (never normalised)
+        const f3 d = mk3(float(a.cam.llc_rel[0] + s * a.cam.horizontal[0] + t * a.cam.vertical[0] - offx),
+                         float(a.cam.llc_rel[1] + s * a.cam.horizontal[1] + t * a.cam.vertical[1] - offy),
+                         float(a.cam.llc_rel[2] + s * a.cam.horizontal[2] + t * a.cam.vertical[2] - offz));
+        const uint32_t e = first + i;
+        store_ray(out, e, a.cam.origin[0] + offx, a.cam.origin[1] + offy, a.cam.origin[2] + offz, d, time, sample_rel << 8, pixel);
+        out.t[e] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     }
 }
 
@@ -183,58 +180,56 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(const __grid_constant
     uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
     FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = ctr->n[QS_EXTEND + parity];
+    const uint32_t n = ctr->n_ext[parity] + wave_new_paths(a, parity);
     if (n == 0) return;
     if (FLAT) {
         flat_stage(a.sc, s_flat[0]);
         __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->rays, (unsigned long long)n);
-    const uint32_t *in_q = a.pool.q[QS_EXTEND + parity];
+    const RayQueue &in = a.pool.ext[parity];
     const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
     const bool has_media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
-    const int free_dest = QS_FREE + parity;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
-        const bool valid = i < n;
-        uint32_t slot = 0;
         int dest = -1;
-        if (valid) {
-            slot = in_q[i];
-            RayC c;
-            const Ray r = load_ray(a.pool, slot, c);
+        Ray r;
+        RayC c;
+        float4 th;
+        HitRec h;
+        if (i < n) {
+            r = load_ray(in, i, c);
+            th = in.t[i];
             MediumRng mr = {0, 0, 0, 0, 0};
             if (has_media) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
-            double t;
-            int leaf;
-            const bool hit = FLAT ? closest_hit_flat<false>(a.sc, s_flat[0], r, mr, t, leaf)
-                                  : closest_hit<false>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
+            const bool hit = FLAT ? closest_hit_flat<false>(a.sc, s_flat[0], r, mr, h.t, h.leaf)
+                                  : closest_hit<false>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, h.t, h.leaf);
             if (hit) {
-                const uint32_t meta = FLAT ? s_flat[0].prims[leaf].meta : __ldg(&a.sc.prims[leaf].meta);
-                const int mat_type = int((meta >> 8) & 15u);
-                if (mat_type == RT1W_MAT_NONE) { // `impl Material for ()`: no emission, no scatter (material.rs:68)
-                    dest = free_dest;
-                } else {
-                    HitRec h;
-                    h.t = t, h.leaf = leaf, h.pad = 0;
-                    a.pool.hit[slot] = h;
-                    dest = mat_type;
-                }
-            } else {
-                dest = free_dest;
+                h.meta = FLAT ? s_flat[0].prims[h.leaf].meta : __ldg(&a.sc.prims[h.leaf].meta);
+                const int mat_type = int((h.meta >> 8) & 15u);
+                if (mat_type != RT1W_MAT_NONE) dest = mat_type; // `impl Material for ()` neither emits nor scatters (material.rs:68)
             }
-            if (dest == free_dest) { // main.rs:113-115 (miss -> background) or a null-material hit (zero radiance)
-                const float4 th = a.pool.thr[slot];
+            if (dest < 0) { // main.rs:113-115 (miss -> background) or a null-material hit (zero radiance): the path ends here
                 const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
                 const bool finite = (fabsf(th.x) + fabsf(th.y) + fabsf(th.z)) < CUDART_INF_F; // false for NaN and inf
                 if (has_background || !finite) splat(a, c.pixel, mk3(th.x, th.y, th.z), rad);
             }
         }
         __syncwarp();
-        warp_sort_push<(1u << (Q_COUNT + 2)) - 1u>(a.pool, dest, slot);
+        const uint32_t e = warp_sort_reserve(ctr, dest);
+        if (dest >= 0) { // hand the ray, its path state and the hit to the material's queue
+            const RayQueue &out = a.pool.mat[dest];
+            out.a[e] = make_double2(r.ox, r.oy);
+            RayB b;
+            b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
+            out.b[e] = b;
+            out.c[e] = c;
+            out.t[e] = th;
+            out.h[e] = h;
+        }
     }
 }
 
@@ -245,7 +240,7 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ DLight s_lights[MAT == RT1W_MAT_LAMBERTIAN ? RT1W_MAX_LIGHTS : 1];
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = ctr->n[QS_MAT + MAT];
+    const uint32_t n = ctr->n_mat[MAT];
     if (n == 0) return;
     // stage the Perlin tables (perlin.rs:7-12) and the light list in shared memory
     const DPerlin *perlins = a.sc.perlins;
@@ -262,32 +257,31 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
     }
     __syncthreads();
 
-    const uint32_t *in_q = a.pool.q[QS_MAT + MAT];
+    const RayQueue &in = a.pool.mat[MAT];
+    const RayQueue &out = a.pool.ext[parity ^ 1];
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
-        const bool valid = i < n;
-        uint32_t slot = 0;
-        bool go_on = false, ended = false;
-        if (valid) {
-            slot = in_q[i];
-            RayC c;
-            const Ray r = load_ray(a.pool, slot, c);
-            const HitRec hr = a.pool.hit[slot];
-            const float4 th4 = a.pool.thr[slot];
-            f3 thr = mk3(th4.x, th4.y, th4.z);
-            const HitInfo h = finalize_hit<false>(a.sc, hr.leaf, r, hr.t);
-            const DMaterial m = a.sc.materials[h.meta >> 12];
+        bool go_on = false;
+        RayC c;
+        f3 thr, dir;
+        float time = 0.0f;
+        HitInfo h;
+        if (i < n) {
+            const Ray r = load_ray(in, i, c);
+            const HitRec hr = in.h[i];
+            const float4 th4 = in.t[i];
+            thr = mk3(th4.x, th4.y, th4.z);
+            const DMaterial m = a.sc.materials[hr.meta >> 12];
+            h = finalize_hit<false>(a.sc, hr.leaf, r, hr.t);
             const uint32_t depth = c.state & 255u;
             if (MAT == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
                 const f3 e = h.front_face ? texture_value(a.sc, perlins, m.texture, h) : mk3(0.0f, 0.0f, 0.0f);
                 splat(a, c.pixel, thr, e);
-                ended = true;
             } else {
                 Rng rng;
                 path_rng_key(a.rp, c.pixel, rng.k0, rng.k1);
                 rng.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), rng.c1 = depth, rng.c2 = purpose_word(a.rp, RNG_SCATTER), rng.block = 0;
-                f3 dir;
-                float time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
+                time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
                 if (MAT == RT1W_MAT_LAMBERTIAN) {
                     const f3 att = texture_value(a.sc, perlins, m.texture, h);
                     f3 weight;
@@ -306,17 +300,18 @@ template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(cons
                 if (depth + 1u >= uint32_t(a.rp.max_depth)) { // main.rs:59-61: the next ray_color call returns black
                     const bool finite = (fabsf(thr.x) + fabsf(thr.y) + fabsf(thr.z)) < CUDART_INF_F; // false for NaN and inf
                     if (!finite) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
-                    ended = true;
                 } else {
-                    store_ray(a.pool, slot, h.px, h.py, h.pz, dir, time, c.state + 1u, c.pixel);
-                    a.pool.thr[slot] = make_float4(thr.x, thr.y, thr.z, 0.0f);
                     go_on = true;
                 }
             }
         }
+        if (MAT == RT1W_MAT_DIFFUSE_LIGHT) continue;
         __syncwarp();
-        warp_sort_push<((1u << QS_FREE) | (1u << (QS_FREE + 1)) | (1u << QS_EXTEND) | (1u << (QS_EXTEND + 1)))>(
-            a.pool, go_on ? QS_EXTEND + (parity ^ 1) : (ended ? QS_FREE + parity : -1), slot);
+        const uint32_t e = warp_reserve(&ctr->n_ext[parity ^ 1], go_on);
+        if (go_on) {
+            store_ray(out, e, h.px, h.py, h.pz, dir, time, c.state + 1u, c.pixel);
+            out.t[e] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+        }
     }
 }
 
@@ -359,29 +354,41 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-cudaError_t pool_alloc(Pool &pool, uint32_t capacity) {
-    pool_free(pool);
+static cudaError_t queue_alloc(RayQueue &q, uint32_t capacity, bool with_hit) {
     cudaError_t e;
-#define RT1W_TRY(x)                                                                                                                                   \
-    if ((e = (x)) != cudaSuccess) {                                                                                                                   \
-        pool_free(pool);                                                                                                                              \
-        return e;                                                                                                                                     \
+    if ((e = cudaMalloc(&q.a, sizeof(double2) * size_t(capacity))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&q.b, sizeof(RayB) * size_t(capacity))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&q.c, sizeof(RayC) * size_t(capacity))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&q.t, sizeof(float4) * size_t(capacity))) != cudaSuccess) return e;
+    if (with_hit && (e = cudaMalloc(&q.h, sizeof(HitRec) * size_t(capacity))) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+static void queue_free(RayQueue &q) {
+    cudaFree(q.a), cudaFree(q.b), cudaFree(q.c), cudaFree(q.t), cudaFree(q.h);
+    q = RayQueue();
+}
+
+// material_mask: only the hit queues of material families the scene uses are allocated.
+cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask) {
+    pool_free(pool);
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = queue_alloc(pool.ext[k], capacity, false);
+    for (int q = 0; q < Q_COUNT && e == cudaSuccess; ++q)
+        if (material_mask & (1 << q)) e = queue_alloc(pool.mat[q], capacity, true);
+    if (e == cudaSuccess) e = cudaMalloc(&pool.ctr, sizeof(Counters));
+    if (e != cudaSuccess) {
+        pool_free(pool);
+        return e;
     }
-    RT1W_TRY(cudaMalloc(&pool.o_xy, sizeof(double2) * size_t(capacity)));
-    RT1W_TRY(cudaMalloc(&pool.o_zd, sizeof(RayB) * size_t(capacity)));
-    RT1W_TRY(cudaMalloc(&pool.dzm, sizeof(RayC) * size_t(capacity)));
-    RT1W_TRY(cudaMalloc(&pool.thr, sizeof(float4) * size_t(capacity)));
-    RT1W_TRY(cudaMalloc(&pool.hit, sizeof(HitRec) * size_t(capacity)));
-    for (int q = 0; q < QS_COUNT; ++q) RT1W_TRY(cudaMalloc(&pool.q[q], sizeof(uint32_t) * size_t(capacity)));
-    RT1W_TRY(cudaMalloc(&pool.ctr, sizeof(Counters)));
-#undef RT1W_TRY
     pool.capacity = capacity;
+    pool.material_mask = material_mask;
     return cudaSuccess;
 }
 
 void pool_free(Pool &pool) {
-    cudaFree(pool.o_xy), cudaFree(pool.o_zd), cudaFree(pool.dzm), cudaFree(pool.thr), cudaFree(pool.hit);
-    for (int q = 0; q < QS_COUNT; ++q) cudaFree(pool.q[q]);
+    for (int k = 0; k < 2; ++k) queue_free(pool.ext[k]);
+    for (int q = 0; q < Q_COUNT; ++q) queue_free(pool.mat[q]);
     cudaFree(pool.ctr);
     pool = Pool();
 }
@@ -436,7 +443,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         for (int k = 0; k < poll_every; ++k, ++wave) {
             const int parity = int(wave & 1);
             mark(K_GENERATE);
-            k_generate<<<gen_blocks, kGenThreads, 0, stream>>>(args, parity, wave == 0 ? 1 : 0);
+            k_generate<<<gen_blocks, kGenThreads, 0, stream>>>(args, parity);
             mark(K_EXTEND);
             if (flat) k_extend<true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
             else k_extend<false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
@@ -459,8 +466,8 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         if ((e = cudaMemcpyAsync(h_ctr, args.pool.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) break;
         drain_marks();
-        // after wave (wave-1): continuing paths sit in q_extend[wave & 1]
-        if (h_ctr->next_path >= args.rp.total_paths && h_ctr->n[QS_EXTEND + (wave & 1)] == 0) break;
+        // after wave (wave-1): continuing rays sit in ext[wave & 1], and next_path[wave & 1] is what wave `wave` would see
+        if (h_ctr->next_path[wave & 1] >= args.rp.total_paths && h_ctr->n_ext[wave & 1] == 0) break;
     }
     for (auto &m : marks) cudaEventDestroy(m.ev);
     for (auto ev : spare) cudaEventDestroy(ev);

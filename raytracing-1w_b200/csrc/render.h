@@ -11,35 +11,35 @@
 namespace rt1w {
 
 // Device-side counters of the wavefront queues (one struct per context, zeroed per render).
-// Queue table: one index space for every queue so that a lane can address "its" queue with a
-// register index into kernel-parameter (constant-bank) arrays.
-enum QueueSlot : int {
-    QS_MAT = 0,             // + rt1w_material_type: hits queued for the shade kernels of the current wave
-    QS_FREE = Q_COUNT,      // + (wave & 1): path slots that terminated during wave w
-    QS_EXTEND = Q_COUNT + 2, // + (wave & 1): rays queued for the extend kernel of wave w
-    QS_COUNT = Q_COUNT + 4
-};
-
 struct Counters {
-    uint32_t n[QS_COUNT];         // entries per queue
-    uint32_t pad[3];
-    unsigned long long next_path; // next (pixel, sample) pair to start
-    unsigned long long rays;      // closest-hit queries so far
+    uint32_t n_ext[2];            // rays that shade kernels of wave w-1 appended to the extend queue of wave w (index w & 1)
+    uint32_t n_mat[Q_COUNT];      // hits queued per material family (rt1w_material_type) for the shade kernels of the current wave
+    uint32_t pad;
+    unsigned long long next_path[2]; // next (pixel, sample) pair to start, as seen by wave w (index w & 1)
+    unsigned long long rays;         // closest-hit queries so far
 };
 
-// Path pool: SoA ray/path state + index queues, all in HBM (DESIGN.md "Data layout").
+// One queue = SoA payload arrays; entry i of every array belongs to the same ray, so a warp reading
+// entries [i, i+32) issues fully coalesced 16-byte-per-lane loads (DESIGN.md "Data layout").
+struct RayQueue {
+    double2 *a = nullptr; // origin.x, origin.y
+    RayB *b = nullptr;    // origin.z, direction.x, direction.y
+    RayC *c = nullptr;    // direction.z, time, state, pixel
+    float4 *t = nullptr;  // throughput rgb (+ unused lane)
+    HitRec *h = nullptr;  // material queues only: t, leaf, meta
+};
+
+// The queues of a render: two extend queues (ping-pong between waves) and one hit queue per material.
+// No path owns a slot: rays move from queue to queue, compacted at every stage.
 struct Pool {
-    double2 *o_xy = nullptr; // origin.x, origin.y
-    RayB *o_zd = nullptr;    // origin.z, direction.x, direction.y
-    RayC *dzm = nullptr;     // direction.z, time, state, pixel
-    float4 *thr = nullptr;   // throughput rgb (+ unused lane)
-    HitRec *hit = nullptr;   // t, leaf
-    uint32_t *q[QS_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // slot-index queues (QueueSlot)
+    RayQueue ext[2];
+    RayQueue mat[Q_COUNT];
     Counters *ctr = nullptr;
-    uint32_t capacity = 0;
+    uint32_t capacity = 0; // rays in flight per wave
+    int material_mask = 0; // material queues allocated
 };
 
-cudaError_t pool_alloc(Pool &pool, uint32_t capacity);
+cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask);
 void pool_free(Pool &pool);
 
 struct RenderArgs {

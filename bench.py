@@ -271,7 +271,7 @@ def main():
             "dtype": "f64 intersection / f32 shading", "data": "synthetic",
             "config": {"workload": "cornel_box 600x600, 100 spp per GPU, depth 50 (main.rs:395-512,867-894; BASELINE.json configs[0])",
                        "sharding": f"sample ranges, rank r renders [{SPP}r, {SPP}(r+1)); NCCL reduce of {n_pixels * 12} B" if world > 1 else "single GPU",
-                       "l2": "flushed between timed iterations (256 MiB memset)", "pool_paths": args.pool or (1 << 20),
+                       "l2": "flushed between timed iterations (256 MiB memset)", "pool_paths": args.pool or (1 << 23),
                        "prims": info.n_prims, "bvh_nodes": info.n_bvh_nodes},
             "mrays_per_s": mrays, "rays_per_path": rays / max(paths, 1.0),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": 312, "d2h_bytes_per_step": n_pixels * 12},

@@ -6,7 +6,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
-LIB_PATH = os.path.join(BUILD_DIR, "librt1w.so")
+LIB_PATH = os.environ.get("RT1W_LIB") or os.path.join(BUILD_DIR, "librt1w.so")  # RT1W_LIB: tuning variants only
 HOST_LIB_PATH = os.path.join(BUILD_DIR, "librt1w_host.so")
 ASSETS_DIR = os.path.join(os.path.dirname(PKG_DIR), "assets")
 

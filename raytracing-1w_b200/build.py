@@ -41,9 +41,10 @@ def _run(cmd):
     subprocess.check_call(cmd, cwd=PKG)
 
 
-def build_product(force=False, extra_flags=()):
+def build_product(force=False, extra_flags=(), variant=None):
+    """variant: builds _build/variant_<variant>.so with extra -D flags (tuning sweeps; select with RT1W_LIB)."""
     os.makedirs(OUT, exist_ok=True)
-    target = os.path.join(OUT, "librt1w.so")
+    target = os.path.join(OUT, "librt1w.so" if not variant else f"variant_{variant}.so")
     deps = [os.path.join(PKG, p) for p in CUDA_SRCS + CUDA_HDRS]
     if force or _stale(target, deps):
         _run([NVCC] + NVCC_FLAGS + list(extra_flags) + ["-o", target] + CUDA_SRCS)
@@ -79,4 +80,8 @@ def build_all(force=False):
 
 
 if __name__ == "__main__":
-    build_all("--force" in sys.argv)
+    if "--variant" in sys.argv:  # python build.py --variant NAME -DRT1W_X=1 ...
+        i = sys.argv.index("--variant")
+        build_product(True, [a for a in sys.argv[i + 2:]], variant=sys.argv[i + 1])
+    else:
+        build_all("--force" in sys.argv)

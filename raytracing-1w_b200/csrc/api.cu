@@ -34,7 +34,7 @@ rt1w_status fail_cuda(const char *what, cudaError_t e) {
         if (e__ != cudaSuccess) return fail_cuda(#call, e__);                                                                                         \
     } while (0)
 
-constexpr uint32_t kDefaultPool = 1u << 20;
+constexpr uint32_t kDefaultPool = 1u << 23; // rays in flight per wave: the queues stream through HBM, so bigger waves amortise launches and the tail
 constexpr int kMaxLeaf = 1; // single-primitive leaves: the f32 leaf-box test screens the f64 primitive solve
 
 template <class T> cudaError_t upload(const std::vector<T> &v, T **out) {
@@ -265,14 +265,18 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     if (p.sample_end - p.sample_begin >= (1 << 24)) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^24-1 samples per pixel in one call");
     if (p.max_depth < 0 || p.max_depth > 255) return fail(RT1W_ERR_UNSUPPORTED, "max_depth must be in [0, 255]");
     if (uint64_t(p.width) * uint64_t(p.height) >= (1ull << 31)) return fail(RT1W_ERR_UNSUPPORTED, "image too large");
-    const uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
-    if (ctx->pool.capacity != want_pool || (ctx->pool.material_mask & scene->material_mask) != scene->material_mask) {
-        cudaError_t e = pool_alloc(ctx->pool, want_pool, scene->material_mask | ctx->pool.material_mask);
+    const uint64_t all_paths = uint64_t(p.width) * uint64_t(p.height) * uint64_t(p.sample_end - p.sample_begin);
+    uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
+    if (p.pool_paths <= 0 && all_paths < want_pool) want_pool = uint32_t((all_paths + 1023u) & ~uint64_t(1023u)); // small renders: one wave holds every path
+    if (ctx->pool.allocated < want_pool || (ctx->pool.material_mask & scene->material_mask) != scene->material_mask) {
+        const uint32_t grow = ctx->pool.allocated > want_pool ? ctx->pool.allocated : want_pool;
+        cudaError_t e = pool_alloc(ctx->pool, grow, scene->material_mask | ctx->pool.material_mask);
         if (e != cudaSuccess) return fail_cuda("path pool allocation", e);
     }
     RenderArgs args;
     args.sc = scene->view;
     args.pool = ctx->pool;
+    args.pool.capacity = want_pool;
     DRenderParams &rp = args.rp;
     rp.width = p.width, rp.height = p.height, rp.sample_begin = p.sample_begin, rp.n_samples = p.sample_end - p.sample_begin;
     rp.max_depth = p.max_depth, rp.flags = p.flags, rp.seed_lo = uint32_t(p.seed), rp.seed_hi = uint32_t(p.seed >> 32);

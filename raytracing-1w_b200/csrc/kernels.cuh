@@ -153,7 +153,12 @@ RT1W_DEV bool hit_rect(const LocalRay &l, int ax, double a0, double a1, double b
     const double dc = ax == 0 ? l.dx : (ax == 1 ? l.dy : l.dz);
     const double oa = ax == 0 ? l.oy : l.ox, da = ax == 0 ? l.dy : l.dx;
     const double ob = ax == 2 ? l.oy : l.oz, db = ax == 2 ? l.dy : l.dz;
-    const double tt = (k - oc) / dc;
+    // t = (k - oc) / dc must land in [tmin, tmax].  Compare before dividing: planes behind the origin,
+    // beyond the current best hit, and the plane the ray starts on (numerator ~ 0, where the f64 division
+    // would take its slow denormal path) leave without paying for the division.
+    const double num = k - oc;
+    if (dc > 0.0 ? (num < tmin * dc || num > tmax * dc) : (dc < 0.0 && (num > tmin * dc || num < tmax * dc))) return false;
+    const double tt = num / dc;
     if (tt < tmin || tt > tmax) return false;
     const double a = oa + tt * da, b = ob + tt * db;
     if (a < a0 || a > a1 || b < b0 || b > b1) return false;

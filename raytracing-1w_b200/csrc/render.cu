@@ -19,9 +19,25 @@
 
 namespace rt1w {
 
+// tunables (overridable at build time for sweeps: build.py --variant NAME -DRT1W_...=N)
+#ifndef RT1W_EXTEND_THREADS
+#define RT1W_EXTEND_THREADS 128
+#endif
+#ifndef RT1W_FLAT_MIN_BLOCKS
+#define RT1W_FLAT_MIN_BLOCKS 4
+#endif
+#ifndef RT1W_BVH_MIN_BLOCKS
+#define RT1W_BVH_MIN_BLOCKS 4
+#endif
+#ifndef RT1W_SHADE_THREADS
+#define RT1W_SHADE_THREADS 128
+#endif
+#ifndef RT1W_GRID_PER_SM
+#define RT1W_GRID_PER_SM 8
+#endif
 constexpr int kGenThreads = 256;
-constexpr int kExtendThreads = 128;
-constexpr int kShadeThreads = 128;
+constexpr int kExtendThreads = RT1W_EXTEND_THREADS;
+constexpr int kShadeThreads = RT1W_SHADE_THREADS;
 
 // ------------------------------------------------------------------------------------------
 // Queue append: the lanes of a warp that hold `pred` get consecutive entries; one atomic per warp.
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // FLAT: scan the primitive list staged in shared memory (scenes of <= kFlatMax primitives) instead of walking the BVH.
 template <bool FLAT>
-__global__ void __launch_bounds__(kExtendThreads) k_extend(const __grid_constant__ RenderArgs a, const int parity, const int material_mask) {
+__global__ void __launch_bounds__(kExtendThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) k_extend(const __grid_constant__ RenderArgs a, const int parity, const int material_mask) {
     // one shared buffer: the staged primitive list (FLAT) or the per-thread traversal stacks (BVH)
     __shared__ __align__(16) unsigned char s_raw[FLAT ? sizeof(FlatScene) : sizeof(uint2) * kStackSmem * kExtendThreads];
     uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
@@ -381,7 +397,7 @@ cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask) {
         pool_free(pool);
         return e;
     }
-    pool.capacity = capacity;
+    pool.capacity = pool.allocated = capacity;
     pool.material_mask = material_mask;
     return cudaSuccess;
 }
@@ -405,7 +421,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     cudaError_t e = cudaMemsetAsync(args.pool.ctr, 0, sizeof(Counters), stream);
     if (e != cudaSuccess) return e;
     // grids: a fixed multiple of the SM count; every kernel grid-strides over a device-side count
-    const int gen_blocks = sm_count * 4, ext_blocks = sm_count * 8, shade_blocks = sm_count * 8;
+    const int gen_blocks = sm_count * 4, ext_blocks = sm_count * RT1W_GRID_PER_SM, shade_blocks = sm_count * RT1W_GRID_PER_SM;
     size_t perlin_bytes = size_t(args.sc.n_perlins) * sizeof(DPerlin);
     const int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
     if (!perlin_in_smem) perlin_bytes = 0;

@@ -35,7 +35,8 @@ struct Pool {
     RayQueue ext[2];
     RayQueue mat[Q_COUNT];
     Counters *ctr = nullptr;
-    uint32_t capacity = 0; // rays in flight per wave
+    uint32_t capacity = 0;  // rays in flight per wave (<= allocated)
+    uint32_t allocated = 0; // entries every queue was allocated with
     int material_mask = 0; // material queues allocated
 };
 

@@ -1,0 +1,75 @@
+"""The C-ABI library loads, exports every symbol include/rt1w.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rt1w.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt1w_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(rt):
+    lib = rt.api.load_library()
+    names = _declared_symbols()
+    assert set(names) == set(rt.api.ABI_SYMBOLS), "api.ABI_SYMBOLS out of date with include/rt1w.h"
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/rt1w.h but not exported by librt1w.so"
+    assert lib.rt1w_abi_version() == 1
+
+
+def test_host_library_exports(rt):
+    h = rt.api.load_host_library()
+    text = open(os.path.join(ROOT, "raytracing-1w_b200", "host", "host_api.h")).read()
+    for name in set(re.findall(r"\b(rt1w_host_[a-z0-9_]+)\s*\(", text)):
+        assert hasattr(h, name)
+
+
+def test_struct_layouts_match_the_header(rt):
+    """ctypes mirrors vs the C compiler's view of include/rt1w.h (sizes probed through a tiny C program)."""
+    import subprocess
+    import tempfile
+
+    api = rt.api
+    src = r'''
+#include <stdio.h>
+#include "rt1w.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt1w_node), sizeof(rt1w_material), sizeof(rt1w_texture),
+         sizeof(rt1w_perlin), sizeof(rt1w_image), sizeof(rt1w_scene_desc), sizeof(rt1w_camera), sizeof(rt1w_render_params),
+         sizeof(rt1w_render_stats), sizeof(rt1w_scene_info), sizeof(rt1w_flat_prim), sizeof(rt1w_ray));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "p"), os.path.join(d, "p.c")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "p")]).split()]
+    mirrors = [api.Node, api.Material, api.Texture, api.Perlin, api.Image, api.SceneDesc, api.Camera, api.RenderParams,
+               api.RenderStats, api.SceneInfo, api.FlatPrim, api.Ray]
+    assert sizes == [C.sizeof(m) for m in mirrors]
+
+
+def test_no_cpu_fallback(rt):
+    """Without a usable CUDA device the product refuses to run (there is no CPU path to fall back to)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rt.api.Rt1wError) as e:
+        rt.api.Context(0)
+    assert e.value.status == rt.api.ERR_NO_DEVICE
+
+
+def test_product_does_not_link_the_oracle(rt):
+    """The shipped library must not depend on the checker."""
+    import subprocess
+
+    out = subprocess.check_output(["ldd", rt.api.LIB_PATH], text=True)
+    assert "oracle" not in out
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", rt.api.LIB_PATH], text=True)
+    assert "oracle_" not in syms

@@ -1,0 +1,47 @@
+"""Throughput of the BASELINE.json configurations other than the headline (parity-test cases, not bench lines).
+
+    python tools/scene_perf.py [scene[:spp] ...]      # prints one JSON line per scene
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+DEFAULT = ["cornel_box:100", "random_scene:32", "final_scene:32", "cornel_smoke:32", "stress:8"]
+
+
+def main():
+    rt = importlib.import_module("raytracing-1w_b200")
+    api = rt.api
+    ctx = api.Context(0)
+    for spec in (sys.argv[1:] or DEFAULT):
+        name, _, spp = spec.partition(":")
+        spp = int(spp or 16)
+        t0 = time.perf_counter()
+        hs = api.HostScene(name, seed=1)
+        t1 = time.perf_counter()
+        scene = api.Scene(ctx, hs.desc)
+        info = scene.info()
+        cam = hs.camera()
+        p = hs.params(spp=spp)
+        scene.render(cam, hs.params(spp=1))  # warm-up (allocations, module load)
+        img, _, st = scene.render(cam, p)
+        pp = hs.params(spp=spp, flags=api.FLAG_PROFILE)
+        _, _, sp = scene.render(cam, pp)
+        print(json.dumps({
+            "scene": name, "image": [p.width, p.height], "spp": spp, "prims": info.n_prims, "bvh_nodes": info.n_bvh_nodes,
+            "bvh_depth": info.bvh_depth, "host_scene_s": round(t1 - t0, 3), "build_ms": round(info.build_ms, 1),
+            "upload_ms": round(info.upload_ms, 1), "render_ms": round(st.render_ms, 2), "mpaths_s": round(st.paths / st.render_ms / 1e3, 1),
+            "mrays_s": round(st.rays / st.render_ms / 1e3, 1), "rays_per_path": round(st.rays / st.paths, 3), "waves": st.waves,
+            "kernel_ms": {api.KERNEL_NAMES[k]: round(sp.kernel_ms[k], 2) for k in range(7) if sp.kernel_launches[k]},
+            "nan_pixels": int((img != img).any(axis=2).sum())}), flush=True)
+        scene.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,5 +1,6 @@
 // api.cu — the C ABI of include/rt1w.h: handles, scene commit (lowering + SAH build + upload),
 // render entry points, the closest-hit parity hook and the host-side output quantisation.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -36,6 +37,33 @@ rt1w_status fail_cuda(const char *what, cudaError_t e) {
 
 constexpr uint32_t kDefaultPool = 1u << 23; // rays in flight per wave: the queues stream through HBM, so bigger waves amortise launches and the tail
 constexpr int kMaxLeaf = 1; // single-primitive leaves: the f32 leaf-box test screens the f64 primitive solve
+
+// Bounds of a lowered primitive in its own frame (the box its wrapper chain rotates and translates).
+void local_bounds(const rt1w_flat_prim &fp, double lo[3], double hi[3]) {
+    const double *p = fp.p;
+    switch (fp.kind) {
+    case RT1W_NODE_XY_RECT:
+    case RT1W_NODE_XZ_RECT:
+    case RT1W_NODE_YZ_RECT: { // in-plane intervals + the reference's +-0.0001 slab (aarect.rs:74-79,112-117,180-185)
+        const int ax = fp.kind == RT1W_NODE_XY_RECT ? 2 : (fp.kind == RT1W_NODE_XZ_RECT ? 1 : 0);
+        const int a = ax == 0 ? 1 : 0, b = ax == 2 ? 1 : 2;
+        lo[a] = p[0], hi[a] = p[1], lo[b] = p[2], hi[b] = p[3], lo[ax] = p[4] - 0.0001, hi[ax] = p[4] + 0.0001;
+        break;
+    }
+    case RT1W_NODE_CONSTANT_MEDIUM:
+        if (fp.boundary != RT1W_NODE_SPHERE) { // p = min xyz, -1/density, max xyz
+            for (int c = 0; c < 3; ++c) lo[c] = p[c], hi[c] = p[4 + c];
+            break;
+        }
+        // fall through: p = center, radius, ...
+    case RT1W_NODE_SPHERE:
+        for (int c = 0; c < 3; ++c) lo[c] = p[c] - p[3], hi[c] = p[c] + p[3];
+        break;
+    default: // not expected (moving spheres keep their world box)
+        for (int c = 0; c < 3; ++c) lo[c] = fp.bbox_min[c], hi[c] = fp.bbox_max[c];
+        break;
+    }
+}
 
 template <class T> cudaError_t upload(const std::vector<T> &v, T **out) {
     *out = nullptr;
@@ -169,14 +197,53 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     if (bvh.depth > kStackSmem + kStackLocal - 2) return fail(RT1W_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
     std::vector<DPrim> dprims(n);
     std::vector<int32_t> prim_id(n);
-    std::vector<float4> prim_boxes(2 * n);
     for (size_t i = 0; i < n; ++i) {
         const rt1w_flat_prim &fp = low.prims[bvh.prim_order[i]];
         dprims[i] = make_device_prim(fp, low.materials);
         prim_id[i] = int32_t(bvh.prim_order[i]);
-        float lo[3], hi[3];
-        conservative_box(fp.bbox_min, fp.bbox_max, lo, hi);
-        prim_boxes[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.0f), prim_boxes[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
+    // Small scenes are scanned, not traversed (kernels.cuh: closest_hit_flat): one padded f32 box per primitive in
+    // the primitive's own frame, listed frame by frame; lo.w = leaf index, hi.w = frame of the BOX (-1 = world).
+    const bool flat = n <= size_t(kFlatMax) && low.frames.size() <= size_t(kFlatMaxFrames);
+    std::vector<float4> prim_boxes;
+    if (flat) {
+        // the scan's FMA-form slab test cancels o/d against plane/d (2^-23 |o| of absolute error per plane) and uses
+        // rcp.approx (2^-23 of the distance travelled): covered for ray origins up to twice the scene's largest
+        // coordinate away from the world origin
+        double reach = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            double llo[3], lhi[3];
+            local_bounds(low.prims[i], llo, lhi);
+            for (int c = 0; c < 3; ++c) {
+                reach = std::max(reach, std::max(std::fabs(low.prims[i].bbox_min[c]), std::fabs(low.prims[i].bbox_max[c])));
+                reach = std::max(reach, std::max(std::fabs(llo[c]), std::fabs(lhi[c])));
+            }
+        }
+        const double scan_pad = 1e-6 * reach;
+        std::vector<int> scan(n);
+        for (size_t i = 0; i < n; ++i) scan[i] = int(i);
+        auto box_frame = [&](int leaf) { // a moving sphere keeps its world box: the reference tests that box (bvh.rs:31) before
+                                         // evaluating the sphere at a time that may lie outside [time0, time1] (main.rs:86)
+            const rt1w_flat_prim &fp = low.prims[bvh.prim_order[leaf]];
+            return fp.kind == RT1W_NODE_MOVING_SPHERE ? -1 : fp.frame;
+        };
+        std::stable_sort(scan.begin(), scan.end(), [&](int a, int b) { return box_frame(a) < box_frame(b); });
+        for (size_t k = 0; k < n; ++k) {
+            const rt1w_flat_prim &fp = low.prims[bvh.prim_order[scan[k]]];
+            const int bf = box_frame(scan[k]);
+            double dlo[3], dhi[3];
+            if (bf < 0) {
+                for (int c = 0; c < 3; ++c) dlo[c] = fp.bbox_min[c], dhi[c] = fp.bbox_max[c];
+            } else {
+                local_bounds(fp, dlo, dhi);
+            }
+            float lo[3], hi[3];
+            conservative_box(dlo, dhi, lo, hi, scan_pad);
+            float4 l = make_float4(lo[0], lo[1], lo[2], 0.0f), h = make_float4(hi[0], hi[1], hi[2], 0.0f);
+            const int32_t leaf = scan[k], frame = bf;
+            std::memcpy(&l.w, &leaf, 4), std::memcpy(&h.w, &frame, 4);
+            prim_boxes.push_back(l), prim_boxes.push_back(h);
+        }
     }
     const auto t1 = std::chrono::steady_clock::now();
 
@@ -229,6 +296,7 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     v.images = s->d_images, v.image_dims = s->d_image_dims, v.lights = s->d_lights;
     v.n_lights = int32_t(low.lights.size()), v.has_lights = low.has_lights ? 1 : 0;
     v.n_prims = int32_t(n), v.n_nodes = int32_t(bvh.nodes.size()), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
+    v.flat = flat ? 1 : 0;
     s->material_mask = low.material_mask;
     s->prims = low.prims;
     s->info.n_prims = int32_t(n), s->info.n_bvh_nodes = int32_t(bvh.nodes.size()), s->info.n_frames = int32_t(low.frames.size());

@@ -126,10 +126,10 @@ struct Builder {
 
 } // namespace
 
-void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3]) {
+void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3], double extra_pad) {
     for (int k = 0; k < 3; ++k) {
         double ext = std::max(hi[k] - lo[k], std::max(std::fabs(lo[k]), std::fabs(hi[k])));
-        double pad = 1e-5 * ext + 1e-5;
+        double pad = 1e-5 * ext + 1e-5 + extra_pad;
         float l = float(lo[k] - pad), h = float(hi[k] + pad);
         out_min[k] = std::nextafter(l, -std::numeric_limits<float>::infinity());
         out_max[k] = std::nextafter(h, std::numeric_limits<float>::infinity());

@@ -25,7 +25,7 @@ struct BvhBuildResult {
 
 // Conservative f32 bounds of an f64 box: padded and rounded outward so that f32 slab arithmetic never
 // culls a primitive the f64 solve would reach.  out = {min.xyz, max.xyz}.
-void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3]);
+void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3], double extra_pad = 0.0);
 
 // bmin/bmax: n x 3 doubles (world-space bounds of the lowered primitives).
 void build_sah_bvh(const double *bmin, const double *bmax, size_t n, int max_leaf, BvhBuildResult &out);

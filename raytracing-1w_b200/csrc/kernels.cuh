@@ -14,6 +14,7 @@
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "device_types.h"
@@ -31,7 +32,7 @@ constexpr int kStackLocal = 40;      // overflow entries (local memory; the buil
 struct SceneView {
     const float4 *nodes;       // 2 x float4 per node
     const DPrim *prims;        // leaf order
-    const float4 *prim_boxes;  // 2 x float4 per primitive (leaf order): its padded f32 bounds
+    const float4 *prim_boxes;  // flat scenes: 2 x float4 per primitive in SCAN order (see FlatScene), else nullptr
     const int32_t *prim_id;    // leaf index -> primitive id (DFS order of the description)
     const DFrame *frames;
     const DMaterial *materials;
@@ -42,6 +43,7 @@ struct SceneView {
     const DLight *lights;
     int32_t n_lights, has_lights;
     int32_t n_prims, n_nodes, n_perlins, n_frames;
+    int32_t flat; // scan the primitive list (closest_hit_flat) instead of walking the BVH
 };
 
 struct f3 {
@@ -98,13 +100,21 @@ struct LocalRay {
     double ox, oy, oz, dx, dy, dz;
 };
 
-RT1W_DEV LocalRay to_local(const SceneView &sc, int frame, const Ray &r) {
+// The rigid part of a wrapper chain: the first 40 bytes of a DFrame (global memory) or its shared-memory copy.
+struct FrameXf {
+    double sin_t, cos_t, bx, by, bz;
+};
+static_assert(offsetof(DFrame, bz) == 32, "FrameXf must alias the head of DFrame");
+
+RT1W_DEV const FrameXf *frame_xf(const SceneView &sc, int frame) { return reinterpret_cast<const FrameXf *>(sc.frames + frame); }
+
+RT1W_DEV LocalRay to_local(const FrameXf *f, const Ray &r) { // f == nullptr: no wrapper chain
     LocalRay l;
-    if (frame < 0) {
+    if (f == nullptr) {
         l.ox = r.ox, l.oy = r.oy, l.oz = r.oz, l.dx = r.dx, l.dy = r.dy, l.dz = r.dz;
         return l;
     }
-    const DFrame *f = sc.frames + frame; // hittable.rs:207 and :241-245, composed on the host
+    // hittable.rs:207 and :241-245, composed on the host
     const double s = f->sin_t, c = f->cos_t;
     l.ox = c * r.ox - s * r.oz + f->bx;
     l.oy = r.oy + f->by;
@@ -145,6 +155,18 @@ RT1W_DEV bool hit_sphere(const LocalRay &l, double cx, double cy, double cz, dou
     return true;
 }
 
+// num / den for a denominator inside the f32 exponent range: f32 reciprocal seed + two f64 Newton corrections
+// (relative error ~1e-16; the IEEE division sequence costs three times as many issue slots).
+RT1W_DEV double div_newton(double num, double den) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(den)));
+    const double r0 = double(rf);
+    double q = num * r0;
+    q = fma(fma(-q, den, num), r0, q);
+    q = fma(fma(-q, den, num), r0, q);
+    return q;
+}
+
 // rect with constant axis ax (0: YZRect, 1: XZRect, 2: XYRect); aarect.rs:46-72,84-110,152-178.
 // The axis is data, not a template parameter: lanes of a warp that test different rectangles
 // (walls, box sides) run the same instruction stream.
@@ -154,11 +176,11 @@ RT1W_DEV bool hit_rect(const LocalRay &l, int ax, double a0, double a1, double b
     const double oa = ax == 0 ? l.oy : l.ox, da = ax == 0 ? l.dy : l.dx;
     const double ob = ax == 2 ? l.oy : l.oz, db = ax == 2 ? l.dy : l.dz;
     // t = (k - oc) / dc must land in [tmin, tmax].  Compare before dividing: planes behind the origin,
-    // beyond the current best hit, and the plane the ray starts on (numerator ~ 0, where the f64 division
-    // would take its slow denormal path) leave without paying for the division.
+    // beyond the current best hit, and the plane the ray starts on leave without paying for the division.
     const double num = k - oc;
     if (dc > 0.0 ? (num < tmin * dc || num > tmax * dc) : (dc < 0.0 && (num > tmin * dc || num < tmax * dc))) return false;
-    const double tt = num / dc;
+    // |dc| tiny or zero: the reference's inf / NaN results (aarect.rs:85-88) come out of the real division
+    const double tt = fabs(dc) > 1e-30 ? div_newton(num, dc) : num / dc;
     if (tt < tmin || tt > tmax) return false;
     const double a = oa + tt * da, b = ob + tt * db;
     if (a < a0 || a > a1 || b < b0 || b > b1) return false;
@@ -184,14 +206,16 @@ RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, d
 
 // One candidate primitive (record at `P`: global memory, or the shared-memory copy of the flat-scan
 // path).  Returns true and the hit parameter when it lands in [t_min, tmax].
-template <bool EXACT>
-RT1W_DEV bool hit_prim(const SceneView &sc, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
+// `flat_frames`: shared-memory copies of the wrapper frames (flat scan) or nullptr (read them from global memory).
+// MEDIA = false compiles the ConstantMedium cases out (scenes without media: no Philox, no f64 slabs in the loop).
+template <bool EXACT, bool MEDIA>
+RT1W_DEV bool hit_prim(const SceneView &sc, const FrameXf *flat_frames, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
     const double2 *w = reinterpret_cast<const double2 *>(P);
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3); // q2 | meta | frame
     const uint32_t meta = uint32_t(tail.z);
     const int type = int(meta & 15u);
     const double2 p01 = w[0], p23 = w[1];
-    const LocalRay l = to_local(sc, tail.w, r);
+    const LocalRay l = to_local(tail.w < 0 ? nullptr : (flat_frames ? flat_frames + tail.w : frame_xf(sc, tail.w)), r);
     switch (type) {
     case P_SPHERE: return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
     case P_MOVING_SPHERE: { // moving_sphere.rs:23-26,31-48
@@ -203,6 +227,7 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DPrim *P, int leaf, const Ray 
     case P_XZ_RECT:
     case P_YZ_RECT: return hit_rect(l, P_YZ_RECT - type, p01.x, p01.y, p23.x, p23.y, w[2].x, kTMin, tmax, t);
     case P_MEDIUM_SPHERE: { // boundary.hit(-inf, inf) then boundary.hit(t1 + 0.0001, inf), constant_medium.rs:58-72
+        if (!MEDIA) return false;
         double r0, r1;
         if (!sphere_roots(l, p01.x, p01.y, p23.x, p23.y, r0, r1)) return false;
         if (r1 < r0 + 0.0001) return false;
@@ -212,6 +237,7 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DPrim *P, int leaf, const Ray 
         return medium_sample<EXACT>(r0, r1, nid, len, kTMin, tmax, mr, id, t);
     }
     case P_MEDIUM_BOX: { // the six sides of aabox.rs:29-76 as three slabs
+        if (!MEDIA) return false;
         const double2 q01 = w[2];
         const double q2 = __hiloint2double(tail.y, tail.x);
         const double ix = 1.0 / l.dx, iy = 1.0 / l.dy, iz = 1.0 / l.dz;
@@ -256,7 +282,7 @@ RT1W_DEV uint32_t node_ref(float4 n0, float4 n1) { return (__float_as_uint(n1.w)
 // (node reference, entry distance) so that subtrees the current best hit already beats are dropped on pop.
 // while-while traversal: every lane descends to its next leaf before any lane runs the (f64) primitive
 // tests, so those run with most of the warp converged.
-template <bool EXACT>
+template <bool EXACT, bool MEDIA>
 RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
     SlabRay s;
     s.ox = float(r.ox), s.oy = float(r.oy), s.oz = float(r.oz);
@@ -313,7 +339,7 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
         const uint32_t first = ref & 0x1fffffffu, count = ref >> 29;
         for (uint32_t i = 0; i < count; ++i) {
             double t;
-            if (hit_prim<EXACT>(sc, sc.prims + (first + i), int(first + i), r, best, mr, t)) {
+            if (hit_prim<EXACT, MEDIA>(sc, nullptr, sc.prims + (first + i), int(first + i), r, best, mr, t)) {
                 best = t, best_leaf = int(first + i);
                 bestf = __double2float_ru(t);
             }
@@ -324,15 +350,26 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
     return best_leaf >= 0;
 }
 
-// Small scenes (<= kFlatMax primitives, e.g. the 13 of the Cornell box): a BVH over a handful of
-// room-sized rectangles culls nothing, so the extend kernel scans the primitive list instead.  The
-// records and their padded f32 boxes sit in shared memory, every lane walks the same primitive at the
-// same time (broadcast reads, no traversal divergence) and the f32 box test screens the f64 solve.
+// Small scenes (<= kFlatMax primitives and <= kFlatMaxFrames wrapper chains, e.g. the 13 + 1 of the Cornell
+// box): a BVH over a handful of room-sized rectangles culls nothing, so the extend kernel scans the primitive
+// list instead.  Records, boxes and frames sit in shared memory.
+//   pass 1 (warp-uniform, f32): every lane slab-tests the same primitive at the same time (broadcast reads, no
+//     divergence).  Boxes are the primitives' bounds in their OWN frame (tight around rotated box sides),
+//     grouped by frame so the ray is re-expressed once per group; the entry distance of every box the ray
+//     crosses beyond t_min is parked in shared memory and the nearest one is tracked.
+//   pass 2 (per lane, f64): solve the nearest candidate, then the nearest remaining one whose box is entered
+//     before the best hit so far (the entry distance is a lower bound of the primitive's t), and so on:
+//     ~1.2 solves per ray.
 constexpr int kFlatMax = 32;
+constexpr int kFlatMaxFrames = 8;
 
 struct FlatScene {
-    DPrim prims[kFlatMax];
-    float4 lo[kFlatMax], hi[kFlatMax];
+    DPrim prims[kFlatMax];             // leaf order
+    float4 lo[kFlatMax], hi[kFlatMax]; // scan order: padded f32 bounds in the frame of the group; lo.w = leaf (int bits)
+    FrameXf frames[kFlatMaxFrames];
+    int32_t group_end[kFlatMaxFrames + 1]; // scan-order groups: group g = boxes [group_end[g-1], group_end[g]) in ...
+    int32_t group_frame[kFlatMaxFrames + 1]; // ... frame group_frame[g] (-1 = world)
+    int32_t n_groups;
 };
 
 RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the whole CTA, then __syncthreads()
@@ -341,29 +378,93 @@ RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the 
     uint32_t *dst = reinterpret_cast<uint32_t *>(fs.prims);
     for (int w = threadIdx.x; w < n * int(sizeof(DPrim) / 4); w += blockDim.x) dst[w] = src[w];
     for (int i = threadIdx.x; i < n; i += blockDim.x) fs.lo[i] = sc.prim_boxes[2 * i], fs.hi[i] = sc.prim_boxes[2 * i + 1];
+    for (int i = threadIdx.x; i < sc.n_frames; i += blockDim.x) fs.frames[i] = *frame_xf(sc, i);
+    if (threadIdx.x == 0) { // the host lists the boxes frame by frame (hi.w = frame of the box)
+        int g = 0;
+        for (int i = 0; i < n; ++i) {
+            const int frame = __float_as_int(sc.prim_boxes[2 * i + 1].w);
+            if (i == 0 || frame != fs.group_frame[g - 1]) fs.group_frame[g++] = frame;
+            fs.group_end[g - 1] = i + 1;
+        }
+        fs.n_groups = g;
+    }
 }
 
-template <bool EXACT>
-RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const Ray &r, const MediumRng &mr, double &t_best, int &leaf_best) {
-    SlabRay s;
-    s.ox = float(r.ox), s.oy = float(r.oy), s.oz = float(r.oz);
-    s.ix = 1.0f / r.dx, s.iy = 1.0f / r.dy, s.iz = 1.0f / r.dz;
+// Slab test in the FMA form t = plane * (1/d) - o * (1/d).  |1/d| is capped at 1e18 so that no product
+// overflows: an axis the ray is parallel to yields -+1e18-scale distances of the right sign instead of
+// inf - inf.  The rounding of the form (cancellation 2^-23 |o / d|, rcp.approx 2^-23 |t|) is covered by the
+// box padding (api.cu: scan_pad), so the comparison itself carries no slack.
+struct SlabRayF {
+    float ix, iy, iz, ox, oy, oz; // 1/d and -o/d
+};
+RT1W_DEV float rcp_capped(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(copysignf(fmaxf(fabsf(d), 1e-18f), d)));
+    return r;
+}
+RT1W_DEV SlabRayF slab_ray(double ox, double oy, double oz, float dx, float dy, float dz) {
+    SlabRayF s;
+    s.ix = rcp_capped(dx), s.iy = rcp_capped(dy), s.iz = rcp_capped(dz);
+    s.ox = -__double2float_rn(ox) * s.ix, s.oy = -__double2float_rn(oy) * s.iy, s.oz = -__double2float_rn(oz) * s.iz;
+    return s;
+}
+constexpr float kTMinSlab = 0.000999f; // just below t_min: a box the ray leaves before t_min cannot hold an accepted root
+RT1W_DEV bool slab_fma(const float4 lo, const float4 hi, const SlabRayF &s, float &tnear) {
+    const float ax = fmaf(lo.x, s.ix, s.ox), bx = fmaf(hi.x, s.ix, s.ox);
+    const float ay = fmaf(lo.y, s.iy, s.oy), by = fmaf(hi.y, s.iy, s.oy);
+    const float az = fmaf(lo.z, s.iz, s.oz), bz = fmaf(hi.z, s.iz, s.oz);
+    tnear = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), kTMinSlab));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return tnear <= tf;
+}
+
+// `tn_col`: this thread's column of the CTA's entry-distance table (stride = blockDim.x floats).
+template <bool EXACT, bool MEDIA>
+RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const Ray &r, const MediumRng &mr, float *tn_col, int stride,
+                               double &t_best, int &leaf_best) {
+    uint32_t cand = 0, bit = 1;
+    float t1 = CUDART_INF_F;
+    int k1 = -1;
+    const int n_groups = fs.n_groups;
+    int k = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int frame = fs.group_frame[g], end = fs.group_end[g];
+        SlabRayF s;
+        if (frame < 0) {
+            s = slab_ray(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
+        } else {
+            const LocalRay l = to_local(fs.frames + frame, r);
+            s = slab_ray(l.ox, l.oy, l.oz, float(l.dx), float(l.dy), float(l.dz));
+        }
+        for (; k < end; ++k, bit <<= 1) {
+            float tn;
+            const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn);
+            tn_col[k * stride] = tn;
+            if (in) cand |= bit;
+            if (in && tn < t1) t1 = tn, k1 = k;
+        }
+    }
     double best = CUDART_INF;
     float bestf = CUDART_INF_F;
     int best_leaf = -1;
-    const int n = sc.n_prims;
-    // pass 1 (warp-uniform): which primitive boxes does this ray cross?
-    uint32_t cand = 0;
-    for (int i = 0; i < n; ++i) {
-        float tn;
-        if (slab(fs.lo[i], fs.hi[i], s, bestf, tn)) cand |= 1u << i;
-    }
-    // pass 2: every lane walks its own candidates; lanes testing different rectangles share one code path
-    while (cand) {
-        const int i = __ffs(int(cand)) - 1;
-        cand &= cand - 1u;
+    k = k1;
+    while (k >= 0) {
+        cand &= ~(1u << k);
+        const int leaf = __float_as_int(fs.lo[k].w);
         double t;
-        if (hit_prim<EXACT>(sc, fs.prims + i, i, r, best, mr, t)) best = t, best_leaf = i;
+        if (hit_prim<EXACT, MEDIA>(sc, fs.frames, fs.prims + leaf, leaf, r, best, mr, t)) {
+            best = t, best_leaf = leaf;
+            bestf = __double2float_ru(t) * 1.000001f;
+        }
+        // next: the nearest remaining box that starts before the best hit; boxes beyond it are dropped for good
+        k = -1;
+        float tb = bestf;
+        for (uint32_t m = cand; m != 0u; m &= m - 1u) {
+            const int c = __ffs(int(m)) - 1;
+            const float tc = tn_col[c * stride];
+            if (tc <= tb) tb = tc, k = c;
+            else if (tc > bestf) cand &= ~(1u << c);
+        }
     }
     t_best = best, leaf_best = best_leaf;
     return best_leaf >= 0;
@@ -404,7 +505,7 @@ template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const SceneView &sc, int l
         h.normal = h.n_out = mk3(1.0f, 0.0f, 0.0f);
         h.front_face = true;
     } else {
-        const LocalRay l = to_local(sc, frame, r);
+        const LocalRay l = to_local(frame < 0 ? nullptr : frame_xf(sc, frame), r);
         const double lx = l.ox + t * l.dx, ly = l.oy + t * l.dy, lz = l.oz + t * l.dz;
         const double2 p01 = __ldg(w), p23 = __ldg(w + 1);
         f3 n;

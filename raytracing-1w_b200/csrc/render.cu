@@ -189,12 +189,15 @@ __global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant_
 // extend
 // ------------------------------------------------------------------------------------------
 // FLAT: scan the primitive list staged in shared memory (scenes of <= kFlatMax primitives) instead of walking the BVH.
-template <bool FLAT>
-__global__ void __launch_bounds__(kExtendThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) k_extend(const __grid_constant__ RenderArgs a, const int parity, const int material_mask) {
+// MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
+template <bool FLAT, bool MEDIA>
+__global__ void __launch_bounds__(kExtendThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) k_extend(const __grid_constant__ RenderArgs a, const int parity) {
     // one shared buffer: the staged primitive list (FLAT) or the per-thread traversal stacks (BVH)
-    __shared__ __align__(16) unsigned char s_raw[FLAT ? sizeof(FlatScene) : sizeof(uint2) * kStackSmem * kExtendThreads];
+    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kExtendThreads;
+    __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kExtendThreads];
     uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
     FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
+    float *s_tn = reinterpret_cast<float *>(s_raw + sizeof(FlatScene)); // entry distances, [primitive][thread]
     Counters *ctr = a.pool.ctr;
     const uint32_t n = ctr->n_ext[parity] + wave_new_paths(a, parity);
     if (n == 0) return;
@@ -205,7 +208,6 @@ __global__ void __launch_bounds__(kExtendThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : 
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->rays, (unsigned long long)n);
     const RayQueue &in = a.pool.ext[parity];
     const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
-    const bool has_media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         int dest = -1;
@@ -217,12 +219,12 @@ __global__ void __launch_bounds__(kExtendThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : 
             r = load_ray(in, i, c);
             th = in.t[i];
             MediumRng mr = {0, 0, 0, 0, 0};
-            if (has_media) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
+            if (MEDIA) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
-            const bool hit = FLAT ? closest_hit_flat<false>(a.sc, s_flat[0], r, mr, h.t, h.leaf)
-                                  : closest_hit<false>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, h.t, h.leaf);
+            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kExtendThreads, h.t, h.leaf)
+                                  : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, h.t, h.leaf);
             if (hit) {
                 h.meta = FLAT ? s_flat[0].prims[h.leaf].meta : __ldg(&a.sc.prims[h.leaf].meta);
                 const int mat_type = int((h.meta >> 8) & 15u);
@@ -339,7 +341,9 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
                                                           float *normal3, uint8_t *front_face, float *uv2) {
     __shared__ uint2 s_stack[kStackSmem * kExtendThreads];
     __shared__ FlatScene s_flat;
-    const bool flat = sc.n_prims <= kFlatMax; // same choice as the render path, so parity covers both traversals
+    float *s_tn = reinterpret_cast<float *>(s_stack); // the flat scan's entry-distance table shares the stack space
+    static_assert(sizeof(float) * kFlatMax <= sizeof(uint2) * kStackSmem, "entry-distance table must fit the stack buffer");
+    const bool flat = sc.flat != 0; // same choice as the render path, so parity covers both traversals
     if (flat) {
         flat_stage(sc, s_flat);
         __syncthreads();
@@ -354,7 +358,8 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
         mr.c0 = uint32_t(i), mr.c1 = uint32_t(uint64_t(i) >> 32), mr.c2 = RNG_TRACE_MEDIUM, mr.k0 = seed_lo, mr.k1 = seed_hi;
         double t;
         int leaf;
-        const bool hit = flat ? closest_hit_flat<true>(sc, s_flat, r, mr, t, leaf) : closest_hit<true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
+        const bool hit = flat ? closest_hit_flat<true, true>(sc, s_flat, r, mr, s_tn + threadIdx.x, kExtendThreads, t, leaf)
+                              : closest_hit<true, true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
         HitInfo h;
         if (hit) h = finalize_hit<true>(sc, leaf, r, t);
         if (prim_id) prim_id[i] = hit ? sc.prim_id[leaf] : -1;
@@ -426,7 +431,8 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     const int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
     if (!perlin_in_smem) perlin_bytes = 0;
     const int poll_every = 8;
-    const bool flat = args.sc.n_prims <= kFlatMax;
+    const bool flat = args.sc.flat != 0;
+    const bool media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
 
     // profiling mode: one event before every launch and one at the end of the chunk
     struct Mark {
@@ -461,8 +467,10 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
             mark(K_GENERATE);
             k_generate<<<gen_blocks, kGenThreads, 0, stream>>>(args, parity);
             mark(K_EXTEND);
-            if (flat) k_extend<true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
-            else k_extend<false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity, material_mask);
+            if (flat && media) k_extend<true, true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
+            else if (flat) k_extend<true, false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
+            else if (media) k_extend<false, true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
+            else k_extend<false, false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
             ws.launches += 2;
 #define RT1W_SHADE(MAT, SMEM, PSM)                                                                                                                    \
     if (material_mask & (1 << MAT)) {                                                                                                                 \

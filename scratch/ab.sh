@@ -1,0 +1,10 @@
+#!/bin/bash
+# A/B: parity tests on the product library, then bench every library given (default: product + all variants)
+python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -15
+for lib in raytracing-1w_b200/_build/librt1w.so raytracing-1w_b200/_build/variant_*.so; do
+  [ -f "$lib" ] || continue
+  RT1W_LIB=$PWD/$lib python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" 2>&1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$lib'.split('/')[-1], 'Mpaths/s',round(d['value'],1),'ms/step',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1), {k:v['ms'] for k,v in d['kernels'].items()})"
+done

@@ -11,8 +11,9 @@ the partial radiance sums are combined with one NCCL reduce.  Prints ONE JSON li
 value   device-resident: scene committed, result left in HBM, timed with CUDA events on the render stream
 e2e     through the C ABI the reference-side host calls (rt1w_render): camera/params in, radiance sums copied
         back to a pinned HOST buffer inside the timed region
-roofline  the extend kernel (closest-hit queries) against the measured HBM peak, on SURVEY.md section 8(d)'s
-        algorithmic bytes per ray segment; kernel time measured live with CUDA events (RT1W_FLAG_PROFILE pass)
+roofline  the wave kernel (scatter + closest hit + regroup, one launch per wave) against the measured HBM peak, on
+        SURVEY.md section 8(d)'s algorithmic bytes (148 B per ray segment + 60 B per path); kernel time measured
+        live with CUDA events around every launch (RT1W_FLAG_PROFILE pass)
 cpu_baseline  the C++ f64 restatement of the reference (oracle/, kind "port": the Rust crate cannot be built in
         this image) on the host cores, on a bounded sample of the same workload
 """
@@ -36,7 +37,6 @@ WIDTH, HEIGHT, SPP, DEPTH = 600, 600, 100, 50
 # algorithmic bytes of one ray segment in a wavefront with fp32 SoA queues
 BYTES_PER_RAY = 148.0       # whole pipeline
 BYTES_PER_PATH = 60.0       # generate write + accumulate
-EXTEND_BYTES_PER_RAY = 40.0 # the extend kernel's share: ray 28 B in, hit 8 B out, queue index 4 B in
 METRIC = "Mpaths/s (Cornell box 600x600, 100 spp per GPU, depth 50)"
 
 
@@ -242,14 +242,14 @@ def main():
                 kernels[name] = {"ms": round(stp.kernel_ms[k], 3), "launches": int(stp.kernel_launches[k]),
                                  "share": round(stp.kernel_ms[k] / ksum, 4)}
         peak, which = measured_peaks()
-        ext_ms = stp.kernel_ms[1]
-        achieved = EXTEND_BYTES_PER_RAY * stp.rays / (ext_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        wave_ms, wave_n = stp.kernel_ms[0], max(stp.kernel_launches[0], 1)
+        alg_bytes = BYTES_PER_RAY * stp.rays + BYTES_PER_PATH * stp.paths  # all launches of one render
+        achieved = alg_bytes / (wave_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_wave", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": which,
-                    "algorithmic_bytes_per_launch": EXTEND_BYTES_PER_RAY * stp.rays / max(stp.kernel_launches[1], 1),
-                    "avg_launch_ms": ext_ms / max(stp.kernel_launches[1], 1),
-                    "pipeline": {"achieved": (BYTES_PER_RAY * stp.rays + BYTES_PER_PATH * stp.paths) / (stp.render_ms * 1e-3) / 1e9,
-                                 "unit": "GB/s", "note": "whole wave loop, 148 B/ray + 60 B/path (SURVEY.md 8d), profiled pass"}}
+                    "algorithmic_bytes_per_launch": alg_bytes / wave_n, "avg_launch_ms": wave_ms / wave_n,
+                    "note": "148 B per ray segment + 60 B per path (SURVEY.md 8d) over all k_wave launches of one render; "
+                            "the kernel moves 160 B per segment through HBM and is bound by instruction issue / latency, see DESIGN.md"}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only): the oracle port on a bounded sample
     cpu = None

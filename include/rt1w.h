@@ -162,10 +162,9 @@ typedef struct rt1w_camera {
 #define RT1W_FLAG_PROFILE 2u /* bracket every kernel launch with CUDA events and fill rt1w_render_stats.kernel_ms (slower) */
 
 /* kernel slots of rt1w_render_stats.kernel_ms / kernel_launches */
-#define RT1W_KERNEL_GENERATE 0
-#define RT1W_KERNEL_EXTEND 1
-#define RT1W_KERNEL_SHADE0 2 /* + rt1w_material_type (LAMBERTIAN .. ISOTROPIC, DIFFUSE_LIGHT) */
-#define RT1W_KERNEL_COUNT 7
+#define RT1W_KERNEL_WAVE 0   /* k_wave: scatter queued hits / start camera paths, closest hit, regroup per material */
+#define RT1W_KERNEL_FINISH 1 /* k_finish: the last sparse waves, every remaining path run to its end by one thread */
+#define RT1W_KERNEL_COUNT 7  /* slots 2..6 reserved */
 
 typedef struct rt1w_render_params {
     int32_t width;          /* image_width  (main.rs:799) */

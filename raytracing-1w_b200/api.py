@@ -71,8 +71,7 @@ class RenderParams(C.Structure):
                 ("stat_clamp", C.c_double), ("pool_paths", C.c_int32), ("reserved", C.c_int32)]
 
 
-KERNEL_NAMES = ["generate", "extend", "shade_lambertian", "shade_metal", "shade_dielectric", "shade_diffuse_light",
-                "shade_isotropic"]  # slot = 2 + rt1w_material_type for the shade kernels
+KERNEL_NAMES = ["wave", "finish", "-", "-", "-", "-", "-"]  # slot = 2 + rt1w_material_type for the shade kernels
 
 
 class RenderStats(C.Structure):

@@ -1,17 +1,26 @@
-// render.cu — the wavefront kernels and the wave loop (sm_100a).
+// render.cu — the wavefront kernel and the wave loop (sm_100a).
 //
-// The reference's pixel loop + recursive ray_color (main.rs:51-190, 957-1001) become, per wave:
+// The reference's pixel loop + recursive ray_color (main.rs:51-190, 957-1001) become a sequence of waves.
+// One wave = ONE launch of k_wave, in which every thread
 //
-//   generate   tops the extend queue up with new camera paths            (main.rs:968-971, camera.rs:61-73)
-//   extend     closest hit per ray, compacts the hits into one queue per material family (bvh.rs:25-50 ...)
-//   shade_<m>  one kernel per material family: scatter + pdf weighting, compacts the surviving rays into
-//              the next wave's extend queue                               (material.rs, pdf.rs)
+//   1. takes one unit of work: a hit queued by the previous wave for one of the scattering material
+//      families (its material decides the scatter code: material.rs, pdf.rs, constant_medium.rs:31-51), or,
+//      past the queued hits, a new camera path (main.rs:968-971, camera.rs:61-73);
+//   2. extends the resulting ray: closest hit over the scene (bvh.rs:25-50 and every `hit()` below it);
+//   3. ends the path there (miss -> background, null material, DiffuseLight -> emission; main.rs:110-115) or
+//      appends ray + path state + hit to the queue of the material it landed on, for the next wave.
 //
-// Ray and path state live in SoA queues in HBM (render.h: RayQueue).  Rays do not own a slot: every
-// stage reads its input queue front to back (fully coalesced 16-byte-per-lane loads) and appends its
-// survivors to the output queue, compacted with __ballot_sync + __popc + __shfl_sync and one atomic
-// per warp per queue.  The recursion `emitted + attenuation * f * L / pdf` is unrolled into a running
-// throughput: only terminal events (DiffuseLight, miss) carry radiance, so a path adds to its pixel once.
+// Ray and path state live in SoA queues in HBM (render.h: RayQueue), one per material family and double
+// buffered between waves.  Rays do not own a slot: a wave reads its input queues front to back (fully
+// coalesced 16-byte-per-lane loads; the queues are laid end to end in the thread index space, each padded
+// to a multiple of 32, so a warp only ever shades one material) and appends the survivors to the output
+// queues, regrouped per material with __ballot_sync + __popc + __shfl_sync and one atomic instruction per
+// warp.  The recursion `emitted + attenuation * f * L / pdf` is unrolled into a running throughput: only
+// terminal events carry radiance, so a path adds to its pixel once.
+//
+// Per ray segment the wave moves 80 B in and 80 B out of HBM (SURVEY.md section 8d counts 148 B for a
+// minimal fp32 wavefront); an earlier split pipeline (generate / extend / one shade kernel per material,
+// 288 B per segment, 7 launches per wave) ran 1.3x slower.
 #include "render.h"
 
 #include <cstdio>
@@ -20,8 +29,8 @@
 namespace rt1w {
 
 // tunables (overridable at build time for sweeps: build.py --variant NAME -DRT1W_...=N)
-#ifndef RT1W_EXTEND_THREADS
-#define RT1W_EXTEND_THREADS 128
+#ifndef RT1W_WAVE_THREADS
+#define RT1W_WAVE_THREADS 128
 #endif
 #ifndef RT1W_FLAT_MIN_BLOCKS
 #define RT1W_FLAT_MIN_BLOCKS 4
@@ -29,44 +38,31 @@ namespace rt1w {
 #ifndef RT1W_BVH_MIN_BLOCKS
 #define RT1W_BVH_MIN_BLOCKS 4
 #endif
-#ifndef RT1W_SHADE_THREADS
-#define RT1W_SHADE_THREADS 128
-#endif
 #ifndef RT1W_GRID_PER_SM
 #define RT1W_GRID_PER_SM 8
 #endif
-constexpr int kGenThreads = 256;
-constexpr int kExtendThreads = RT1W_EXTEND_THREADS;
-constexpr int kShadeThreads = RT1W_SHADE_THREADS;
+constexpr int kWaveThreads = RT1W_WAVE_THREADS;
+constexpr int kExtendThreads = kWaveThreads; // k_trace shares the traversal-stack geometry
 
-// ------------------------------------------------------------------------------------------
-// Queue append: the lanes of a warp that hold `pred` get consecutive entries; one atomic per warp.
-// ------------------------------------------------------------------------------------------
-RT1W_DEV uint32_t warp_reserve(uint32_t *counter, bool pred) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0) return 0;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(m & ((1u << lane) - 1u));
-}
+// Scattering material families, in the order their queues are laid out in a wave's thread index space.
+__host__ __device__ constexpr int scatter_mat(int s) { return s < 3 ? s : int(RT1W_MAT_ISOTROPIC); } // LAMBERTIAN, METAL, DIELECTRIC, ISOTROPIC
+static_assert(RT1W_MAT_LAMBERTIAN == 0 && RT1W_MAT_METAL == 1 && RT1W_MAT_DIELECTRIC == 2, "segment order");
 
 // Sorts the lanes of a warp into the per-material hit queues with ONE atomic instruction: lane q
 // reserves queue q's entries for the whole warp (Q_COUNT lanes, Q_COUNT addresses, one round trip),
 // then every lane fetches the base of its own destination with a shuffle.  dest < 0: nothing to append.
-RT1W_DEV uint32_t warp_sort_reserve(Counters *ctr, int dest) {
+RT1W_DEV uint32_t warp_sort_reserve(uint32_t *n_mat, int dest) {
     const int lane = threadIdx.x & 31;
     uint32_t mine = 0, count_for_lane = 0;
 #pragma unroll
     for (int q = 0; q < Q_COUNT; ++q) {
+        if (q == RT1W_MAT_DIFFUSE_LIGHT) continue; // lights end the path inside the wave
         const unsigned m = __ballot_sync(0xffffffffu, dest == q);
         if (dest == q) mine = m;
         if (lane == q) count_for_lane = uint32_t(__popc(m));
     }
     uint32_t base = 0;
-    if (count_for_lane) base = atomicAdd(&ctr->n_mat[lane], count_for_lane);
+    if (count_for_lane) base = atomicAdd(&n_mat[lane], count_for_lane);
     base = __shfl_sync(0xffffffffu, base, dest < 0 ? 0 : dest);
     return base + __popc(mine & ((1u << lane) - 1u));
 }
@@ -93,6 +89,7 @@ RT1W_DEV void splat(const RenderArgs &a, uint32_t pixel, f3 thr, f3 radiance) {
         }
     }
 }
+RT1W_DEV bool finite3(f3 v) { return (fabsf(v.x) + fabsf(v.y) + fabsf(v.z)) < CUDART_INF_F; } // false for NaN and inf
 
 RT1W_DEV Ray load_ray(const RayQueue &q, uint32_t i, RayC &c) {
     const double2 a = q.a[i];
@@ -105,16 +102,6 @@ RT1W_DEV Ray load_ray(const RayQueue &q, uint32_t i, RayC &c) {
     return r;
 }
 
-RT1W_DEV void store_ray(const RayQueue &q, uint32_t i, double ox, double oy, double oz, f3 d, float time, uint32_t state, uint32_t pixel) {
-    q.a[i] = make_double2(ox, oy);
-    RayB b;
-    b.oz = oz, b.dx = d.x, b.dy = d.y;
-    q.b[i] = b;
-    RayC c;
-    c.dz = d.z, c.time = time, c.state = state, c.pixel = pixel;
-    q.c[i] = c;
-}
-
 // Philox key/counter of a path: key = (reference pixel seed j*w+i (main.rs:964), seed), counter = (sample, bounce, purpose, block)
 RT1W_DEV void path_rng_key(const DRenderParams &rp, uint32_t pixel, uint32_t &k0, uint32_t &k1) {
     const uint32_t row = pixel / uint32_t(rp.width), col = pixel - row * uint32_t(rp.width);
@@ -124,213 +111,213 @@ RT1W_DEV void path_rng_key(const DRenderParams &rp, uint32_t pixel, uint32_t &k0
 }
 RT1W_DEV uint32_t purpose_word(const DRenderParams &rp, uint32_t stream) { return stream ^ (rp.seed_hi << 4); }
 
-// Rays of wave w: what the shade kernels of wave w-1 appended plus what generate(w) adds on top.
-RT1W_DEV uint32_t wave_new_paths(const RenderArgs &a, int parity) {
-    const Counters *ctr = a.pool.ctr;
-    const unsigned long long left = a.rp.total_paths - min(a.rp.total_paths, ctr->next_path[parity]);
-    const uint32_t room = a.pool.capacity - ctr->n_ext[parity];
-    return uint32_t(min((unsigned long long)room, left));
-}
-
 // ------------------------------------------------------------------------------------------
-// generate
+// a new camera path (main.rs:968-971, camera.rs:61-73, math.rs:30-37)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGenThreads) k_generate(const __grid_constant__ RenderArgs a, const int parity) {
-    Counters *ctr = a.pool.ctr;
-    const uint32_t first = ctr->n_ext[parity];
-    const unsigned long long path0 = ctr->next_path[parity];
-    const uint32_t n = wave_new_paths(a, parity);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { // hand the counters of the next wave over; nobody else touches them now
-#pragma unroll
-        for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[q] = 0;
-        ctr->n_ext[parity ^ 1] = 0;
-        ctr->next_path[parity ^ 1] = path0 + n;
-    }
-    const RayQueue &out = a.pool.ext[parity];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long k = path0 + i;
-        const uint32_t sample_rel = uint32_t(k / a.rp.n_pixels);
-        const uint32_t pixel = uint32_t(k - (unsigned long long)sample_rel * a.rp.n_pixels);
-        const uint32_t row = pixel / uint32_t(a.rp.width), col = pixel - row * uint32_t(a.rp.width);
-        const uint32_t j = uint32_t(a.rp.height) - 1u - row; // main.rs:959: rows are emitted top first
-        Rng rng;
-        path_rng_key(a.rp, pixel, rng.k0, rng.k1);
-        rng.c0 = uint32_t(a.rp.sample_begin) + sample_rel, rng.c1 = 0, rng.c2 = purpose_word(a.rp, RNG_CAMERA), rng.block = 0;
-        const Philox4 x = rng.next4();
-        const double s = (double(col) + double(u01(x.x))) / double(a.rp.width - 1);  // main.rs:968
-        const double t = (double(j) + double(u01(x.y))) / double(a.rp.height - 1);   // main.rs:969
-        const float time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01(x.z);     // camera.rs:71
-        double offx = 0.0, offy = 0.0, offz = 0.0;
-        if (a.cam.lens_radius != 0.0) { // camera.rs:62-63; the rejection loop of math.rs:30-37
-            float px, py;
-            for (;;) {
-                const Philox4 y = rng.next4();
-                px = 2.0f * u01(y.x) - 1.0f, py = 2.0f * u01(y.y) - 1.0f;
-                if (px * px + py * py < 1.0f) break;
-                px = 2.0f * u01(y.z) - 1.0f, py = 2.0f * u01(y.w) - 1.0f;
-                if (px * px + py * py < 1.0f) break;
-            }
-            const double rx = a.cam.lens_radius * double(px), ry = a.cam.lens_radius * double(py);
-            offx = a.cam.u[0] * rx + a.cam.v[0] * ry;
-            offy = a.cam.u[1] * rx + a.cam.v[1] * ry;
-            offz = a.cam.u[2] * rx + a.cam.v[2] * ry;
+RT1W_DEV Ray generate_ray(const RenderArgs &a, unsigned long long k, uint32_t &state, uint32_t &pixel_out) {
+    const uint32_t sample_rel = uint32_t(k / a.rp.n_pixels);
+    const uint32_t pixel = uint32_t(k - (unsigned long long)sample_rel * a.rp.n_pixels);
+    const uint32_t row = pixel / uint32_t(a.rp.width), col = pixel - row * uint32_t(a.rp.width);
+    const uint32_t j = uint32_t(a.rp.height) - 1u - row; // main.rs:959: rows are emitted top first
+    Rng rng;
+    rng.k0 = j * uint32_t(a.rp.width) + col, rng.k1 = a.rp.seed_lo;
+    rng.c0 = uint32_t(a.rp.sample_begin) + sample_rel, rng.c1 = 0, rng.c2 = purpose_word(a.rp, RNG_CAMERA), rng.block = 0;
+    const Philox4 x = rng.next4();
+    const double s = (double(col) + double(u01(x.x))) / double(a.rp.width - 1);  // main.rs:968
+    const double t = (double(j) + double(u01(x.y))) / double(a.rp.height - 1);   // main.rs:969
+    double offx = 0.0, offy = 0.0, offz = 0.0;
+    if (a.cam.lens_radius != 0.0) { // camera.rs:62-63; the rejection loop of math.rs:30-37
+        float px, py;
+        for (;;) {
+            const Philox4 y = rng.next4();
+            px = 2.0f * u01(y.x) - 1.0f, py = 2.0f * u01(y.y) - 1.0f;
+            if (px * px + py * py < 1.0f) break;
+            px = 2.0f * u01(y.z) - 1.0f, py = 2.0f * u01(y.w) - 1.0f;
+            if (px * px + py * py < 1.0f) break;
         }
-        // camera.rs:67-70: direction = lower_left_corner + s*horizontal + t*vertical - origin - offset (never normalised)
-        const f3 d = mk3(float(a.cam.llc_rel[0] + s * a.cam.horizontal[0] + t * a.cam.vertical[0] - offx),
-                         float(a.cam.llc_rel[1] + s * a.cam.horizontal[1] + t * a.cam.vertical[1] - offy),
-                         float(a.cam.llc_rel[2] + s * a.cam.horizontal[2] + t * a.cam.vertical[2] - offz));
-        const uint32_t e = first + i;
-        store_ray(out, e, a.cam.origin[0] + offx, a.cam.origin[1] + offy, a.cam.origin[2] + offz, d, time, sample_rel << 8, pixel);
-        out.t[e] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        const double rx = a.cam.lens_radius * double(px), ry = a.cam.lens_radius * double(py);
+        offx = a.cam.u[0] * rx + a.cam.v[0] * ry;
+        offy = a.cam.u[1] * rx + a.cam.v[1] * ry;
+        offz = a.cam.u[2] * rx + a.cam.v[2] * ry;
     }
+    Ray r;
+    // camera.rs:67-70: direction = lower_left_corner + s*horizontal + t*vertical - origin - offset (never normalised)
+    r.dx = float(a.cam.llc_rel[0] + s * a.cam.horizontal[0] + t * a.cam.vertical[0] - offx);
+    r.dy = float(a.cam.llc_rel[1] + s * a.cam.horizontal[1] + t * a.cam.vertical[1] - offy);
+    r.dz = float(a.cam.llc_rel[2] + s * a.cam.horizontal[2] + t * a.cam.vertical[2] - offz);
+    r.ox = a.cam.origin[0] + offx, r.oy = a.cam.origin[1] + offy, r.oz = a.cam.origin[2] + offz;
+    r.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01(x.z); // camera.rs:71
+    state = sample_rel << 8;
+    pixel_out = pixel;
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------
-// extend
+// scatter at a queued hit: one instantiation per scattering material family.  Rewrites `r` into the
+// scattered ray, advances the depth in c.state and folds the attenuation into `thr`.  Returns false when
+// the path ends here (depth limit, main.rs:59-61).
 // ------------------------------------------------------------------------------------------
-// FLAT: scan the primitive list staged in shared memory (scenes of <= kFlatMax primitives) instead of walking the BVH.
+template <int MAT>
+RT1W_DEV bool scatter(const RenderArgs &a, const DPerlin *perlins, const DLight *lights, Ray &r, const HitRec &hr, RayC &c, f3 &thr) {
+    const DMaterial m = a.sc.materials[hr.meta >> 12];
+    const HitInfo h = finalize_hit<false>(a.sc, hr.leaf, r, hr.t);
+    const uint32_t depth = c.state & 255u;
+    Rng rng;
+    path_rng_key(a.rp, c.pixel, rng.k0, rng.k1);
+    rng.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), rng.c1 = depth, rng.c2 = purpose_word(a.rp, RNG_SCATTER), rng.block = 0;
+    f3 dir;
+    float time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
+    if (MAT == RT1W_MAT_LAMBERTIAN) {
+        const f3 att = texture_value(a.sc, perlins, m.texture, h);
+        f3 weight;
+        dir = scatter_lambertian(a.sc, lights, h, rng, weight);
+        thr = thr * att * weight;
+        time = float(hr.t); // main.rs:86,145: the scattered ray's time is the hit parameter t
+    } else if (MAT == RT1W_MAT_METAL) {
+        dir = scatter_metal(m, r, h, rng);
+        thr = thr * mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
+    } else if (MAT == RT1W_MAT_DIELECTRIC) {
+        dir = scatter_dielectric(m, r, h, rng); // attenuation (1,1,1)
+    } else {                                    // Isotropic, constant_medium.rs:36-51
+        thr = thr * texture_value(a.sc, perlins, m.texture, h);
+        dir = random_in_unit_sphere(rng);
+    }
+    if (depth + 1u >= uint32_t(a.rp.max_depth)) { // main.rs:59-61: the next ray_color call returns black
+        if (!finite3(thr)) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
+        return false;
+    }
+    r.ox = h.px, r.oy = h.py, r.oz = h.pz;
+    r.dx = dir.x, r.dy = dir.y, r.dz = dir.z;
+    r.time = time;
+    c.state += 1u;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// the wave kernel
+// ------------------------------------------------------------------------------------------
+// FLAT: scan the primitive list staged in shared memory (small scenes) instead of walking the BVH.
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 template <bool FLAT, bool MEDIA>
-__global__ void __launch_bounds__(kExtendThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) k_extend(const __grid_constant__ RenderArgs a, const int parity) {
-    // one shared buffer: the staged primitive list (FLAT) or the per-thread traversal stacks (BVH)
-    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kExtendThreads;
-    __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kExtendThreads];
+__global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS)
+    k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
+    extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
+    // one static buffer: the staged primitive list + entry-distance table (FLAT) or the per-thread traversal stacks (BVH)
+    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kWaveThreads;
+    __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kWaveThreads];
+    __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
+    __shared__ unsigned int s_traced;
     uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
     FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
     float *s_tn = reinterpret_cast<float *>(s_raw + sizeof(FlatScene)); // entry distances, [primitive][thread]
-    Counters *ctr = a.pool.ctr;
-    const uint32_t n = ctr->n_ext[parity] + wave_new_paths(a, parity);
-    if (n == 0) return;
-    if (FLAT) {
-        flat_stage(a.sc, s_flat[0]);
-        __syncthreads();
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->rays, (unsigned long long)n);
-    const RayQueue &in = a.pool.ext[parity];
-    const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + threadIdx.x;
-        int dest = -1;
-        Ray r;
-        RayC c;
-        float4 th;
-        HitRec h;
-        if (i < n) {
-            r = load_ray(in, i, c);
-            th = in.t[i];
-            MediumRng mr = {0, 0, 0, 0, 0};
-            if (MEDIA) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
-                path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
-                mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
-            }
-            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kExtendThreads, h.t, h.leaf)
-                                  : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kExtendThreads, h.t, h.leaf);
-            if (hit) {
-                h.meta = FLAT ? s_flat[0].prims[h.leaf].meta : __ldg(&a.sc.prims[h.leaf].meta);
-                const int mat_type = int((h.meta >> 8) & 15u);
-                if (mat_type != RT1W_MAT_NONE) dest = mat_type; // `impl Material for ()` neither emits nor scatters (material.rs:68)
-            }
-            if (dest < 0) { // main.rs:113-115 (miss -> background) or a null-material hit (zero radiance): the path ends here
-                const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
-                const bool finite = (fabsf(th.x) + fabsf(th.y) + fabsf(th.z)) < CUDART_INF_F; // false for NaN and inf
-                if (has_background || !finite) splat(a, c.pixel, mk3(th.x, th.y, th.z), rad);
-            }
-        }
-        __syncwarp();
-        const uint32_t e = warp_sort_reserve(ctr, dest);
-        if (dest >= 0) { // hand the ray, its path state and the hit to the material's queue
-            const RayQueue &out = a.pool.mat[dest];
-            out.a[e] = make_double2(r.ox, r.oy);
-            RayB b;
-            b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
-            out.b[e] = b;
-            out.c[e] = c;
-            out.t[e] = th;
-            out.h[e] = h;
-        }
-    }
-}
 
-// ------------------------------------------------------------------------------------------
-// shade: one instantiation per material family
-// ------------------------------------------------------------------------------------------
-template <int MAT> __global__ void __launch_bounds__(kShadeThreads) k_shade(const __grid_constant__ RenderArgs a, const int parity, const int perlin_in_smem) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    __shared__ DLight s_lights[MAT == RT1W_MAT_LAMBERTIAN ? RT1W_MAX_LIGHTS : 1];
     Counters *ctr = a.pool.ctr;
-    const uint32_t n = ctr->n_mat[MAT];
-    if (n == 0) return;
-    // stage the Perlin tables (perlin.rs:7-12) and the light list in shared memory
+    const int nxt = slot == 2 ? 0 : slot + 1, clr = nxt == 2 ? 0 : nxt + 1;
+    // the thread index space of the wave: [lambertian hits | metal | dielectric | isotropic | new paths], each hit
+    // segment padded to whole warps
+    const uint32_t cnt0 = ctr->n_mat[slot][scatter_mat(0)], cnt1 = ctr->n_mat[slot][scatter_mat(1)];
+    const uint32_t cnt2 = ctr->n_mat[slot][scatter_mat(2)], cnt3 = ctr->n_mat[slot][scatter_mat(3)];
+    const uint32_t off1 = (cnt0 + 31u) & ~31u, off2 = off1 + ((cnt1 + 31u) & ~31u), off3 = off2 + ((cnt2 + 31u) & ~31u);
+    const uint32_t off4 = off3 + ((cnt3 + 31u) & ~31u);
+    const uint32_t queued = cnt0 + cnt1 + cnt2 + cnt3;
+    const unsigned long long path0 = ctr->next_path[slot];
+    const unsigned long long left = a.rp.total_paths - min(a.rp.total_paths, path0);
+    const uint32_t n_new = uint32_t(min((unsigned long long)(a.pool.capacity - min(a.pool.capacity, queued)), left));
+    const uint32_t total = off4 + n_new;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // hand the counters over: nobody else writes these slots during this wave
+        ctr->next_path[nxt] = path0 + n_new;
+#pragma unroll
+        for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[clr][q] = 0;
+    }
+    if (blockIdx.x * blockDim.x >= total) return;
+
+    if (threadIdx.x == 0) s_traced = 0;
+    if (FLAT) flat_stage(a.sc, s_flat[0]);
     const DPerlin *perlins = a.sc.perlins;
-    constexpr bool kTextured = MAT == RT1W_MAT_LAMBERTIAN || MAT == RT1W_MAT_ISOTROPIC || MAT == RT1W_MAT_DIFFUSE_LIGHT;
-    if (kTextured && perlin_in_smem) {
+    if (perlin_in_smem) {
         const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
         for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
         perlins = reinterpret_cast<const DPerlin *>(s_dyn);
     }
-    if (MAT == RT1W_MAT_LAMBERTIAN) {
-        for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
-    }
+    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
     __syncthreads();
 
-    const RayQueue &in = a.pool.mat[MAT];
-    const RayQueue &out = a.pool.ext[parity ^ 1];
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
+    uint32_t traced = 0;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
-        bool go_on = false;
+        Ray r;
         RayC c;
-        f3 thr, dir;
-        float time = 0.0f;
-        HitInfo h;
-        if (i < n) {
-            const Ray r = load_ray(in, i, c);
-            const HitRec hr = in.h[i];
-            const float4 th4 = in.t[i];
-            thr = mk3(th4.x, th4.y, th4.z);
-            const DMaterial m = a.sc.materials[hr.meta >> 12];
-            h = finalize_hit<false>(a.sc, hr.leaf, r, hr.t);
-            const uint32_t depth = c.state & 255u;
-            if (MAT == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
-                const f3 e = h.front_face ? texture_value(a.sc, perlins, m.texture, h) : mk3(0.0f, 0.0f, 0.0f);
+        f3 thr;
+        bool alive = false;
+        if (i < off4) { // a hit queued by the previous wave: scatter
+            const int seg = i < off1 ? 0 : (i < off2 ? 1 : (i < off3 ? 2 : 3)); // warp-uniform
+            const uint32_t j = i - (seg == 0 ? 0u : (seg == 1 ? off1 : (seg == 2 ? off2 : off3)));
+            if (j < (seg == 0 ? cnt0 : (seg == 1 ? cnt1 : (seg == 2 ? cnt2 : cnt3)))) {
+                const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
+                r = load_ray(in, j, c);
+                const HitRec hr = in.h[j];
+                const float4 th4 = in.t[j];
+                thr = mk3(th4.x, th4.y, th4.z);
+                if (seg == 0) alive = scatter<RT1W_MAT_LAMBERTIAN>(a, perlins, s_lights, r, hr, c, thr);
+                else if (seg == 1) alive = scatter<RT1W_MAT_METAL>(a, perlins, s_lights, r, hr, c, thr);
+                else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, perlins, s_lights, r, hr, c, thr);
+                else alive = scatter<RT1W_MAT_ISOTROPIC>(a, perlins, s_lights, r, hr, c, thr);
+            }
+        } else if (i < total) { // a new camera path
+            r = generate_ray(a, path0 + (i - off4), c.state, c.pixel);
+            thr = mk3(1.0f, 1.0f, 1.0f);
+            alive = true;
+        }
+
+        int dest = -1;
+        HitRec h;
+        if (alive) { // extend: closest hit, then end the path or hand it to the material it landed on
+            ++traced;
+            MediumRng mr = {0, 0, 0, 0, 0};
+            if (MEDIA) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
+                path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
+                mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
+            }
+            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kWaveThreads, h.t, h.leaf)
+                                  : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
+            int mat_type = RT1W_MAT_NONE;
+            if (hit) {
+                h.meta = FLAT ? s_flat[0].prims[h.leaf].meta : __ldg(&a.sc.prims[h.leaf].meta);
+                mat_type = int((h.meta >> 8) & 15u);
+            }
+            if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
+                const HitInfo hi = finalize_hit<false>(a.sc, h.leaf, r, h.t);
+                const f3 e = hi.front_face ? texture_value(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
                 splat(a, c.pixel, thr, e);
+            } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
+                const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
+                if (has_background || !finite3(thr)) splat(a, c.pixel, thr, rad);
             } else {
-                Rng rng;
-                path_rng_key(a.rp, c.pixel, rng.k0, rng.k1);
-                rng.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), rng.c1 = depth, rng.c2 = purpose_word(a.rp, RNG_SCATTER), rng.block = 0;
-                time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
-                if (MAT == RT1W_MAT_LAMBERTIAN) {
-                    const f3 att = texture_value(a.sc, perlins, m.texture, h);
-                    f3 weight;
-                    dir = scatter_lambertian(a.sc, s_lights, h, rng, weight);
-                    thr = thr * att * weight;
-                    time = float(hr.t); // main.rs:86,145: the scattered ray's time is the hit parameter t
-                } else if (MAT == RT1W_MAT_METAL) {
-                    dir = scatter_metal(m, r, h, rng);
-                    thr = thr * mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
-                } else if (MAT == RT1W_MAT_DIELECTRIC) {
-                    dir = scatter_dielectric(m, r, h, rng); // attenuation (1,1,1)
-                } else {                                    // Isotropic, constant_medium.rs:36-51
-                    thr = thr * texture_value(a.sc, perlins, m.texture, h);
-                    dir = random_in_unit_sphere(rng);
-                }
-                if (depth + 1u >= uint32_t(a.rp.max_depth)) { // main.rs:59-61: the next ray_color call returns black
-                    const bool finite = (fabsf(thr.x) + fabsf(thr.y) + fabsf(thr.z)) < CUDART_INF_F; // false for NaN and inf
-                    if (!finite) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
-                } else {
-                    go_on = true;
-                }
+                dest = mat_type;
             }
         }
-        if (MAT == RT1W_MAT_DIFFUSE_LIGHT) continue;
         __syncwarp();
-        const uint32_t e = warp_reserve(&ctr->n_ext[parity ^ 1], go_on);
-        if (go_on) {
-            store_ray(out, e, h.px, h.py, h.pz, dir, time, c.state + 1u, c.pixel);
+        const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
+        if (dest >= 0) { // ray + path state + hit go to the queue of the material the ray landed on
+            const RayQueue &out = a.pool.mat[parity ^ 1][dest];
+            out.a[e] = make_double2(r.ox, r.oy);
+            RayB b;
+            b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
+            out.b[e] = b;
+            c.dz = r.dz, c.time = r.time;
+            out.c[e] = c;
             out.t[e] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+            out.h[e] = h;
         }
     }
+    // closest-hit queries of this wave -> the render's ray count
+    traced = __reduce_add_sync(0xffffffffu, traced);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(&s_traced, traced);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_traced) atomicAdd(&ctr->rays, (unsigned long long)s_traced);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -375,13 +362,13 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static cudaError_t queue_alloc(RayQueue &q, uint32_t capacity, bool with_hit) {
+static cudaError_t queue_alloc(RayQueue &q, uint32_t capacity) {
     cudaError_t e;
     if ((e = cudaMalloc(&q.a, sizeof(double2) * size_t(capacity))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&q.b, sizeof(RayB) * size_t(capacity))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&q.c, sizeof(RayC) * size_t(capacity))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&q.t, sizeof(float4) * size_t(capacity))) != cudaSuccess) return e;
-    if (with_hit && (e = cudaMalloc(&q.h, sizeof(HitRec) * size_t(capacity))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&q.h, sizeof(HitRec) * size_t(capacity))) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -390,13 +377,13 @@ static void queue_free(RayQueue &q) {
     q = RayQueue();
 }
 
-// material_mask: only the hit queues of material families the scene uses are allocated.
+// material_mask: only the hit queues of the scattering material families the scene uses are allocated.
 cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask) {
     pool_free(pool);
     cudaError_t e = cudaSuccess;
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = queue_alloc(pool.ext[k], capacity, false);
-    for (int q = 0; q < Q_COUNT && e == cudaSuccess; ++q)
-        if (material_mask & (1 << q)) e = queue_alloc(pool.mat[q], capacity, true);
+    for (int k = 0; k < 2; ++k)
+        for (int q = 0; q < Q_COUNT && e == cudaSuccess; ++q)
+            if ((material_mask & (1 << q)) && q != RT1W_MAT_DIFFUSE_LIGHT) e = queue_alloc(pool.mat[k][q], capacity);
     if (e == cudaSuccess) e = cudaMalloc(&pool.ctr, sizeof(Counters));
     if (e != cudaSuccess) {
         pool_free(pool);
@@ -408,25 +395,17 @@ cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask) {
 }
 
 void pool_free(Pool &pool) {
-    for (int k = 0; k < 2; ++k) queue_free(pool.ext[k]);
-    for (int q = 0; q < Q_COUNT; ++q) queue_free(pool.mat[q]);
+    for (int k = 0; k < 2; ++k)
+        for (int q = 0; q < Q_COUNT; ++q) queue_free(pool.mat[k][q]);
     cudaFree(pool.ctr);
     pool = Pool();
 }
 
-namespace {
-
-template <int MAT> void launch_shade(const RenderArgs &args, int parity, int blocks, size_t smem, int perlin_in_smem, cudaStream_t stream) {
-    k_shade<MAT><<<blocks, kShadeThreads, smem, stream>>>(args, parity, perlin_in_smem);
-}
-
-} // namespace
-
 cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_ctr, cudaStream_t stream, int sm_count, WaveStats &ws) {
     cudaError_t e = cudaMemsetAsync(args.pool.ctr, 0, sizeof(Counters), stream);
     if (e != cudaSuccess) return e;
-    // grids: a fixed multiple of the SM count; every kernel grid-strides over a device-side count
-    const int gen_blocks = sm_count * 4, ext_blocks = sm_count * RT1W_GRID_PER_SM, shade_blocks = sm_count * RT1W_GRID_PER_SM;
+    // grid: a fixed multiple of the SM count; the kernel grid-strides over a device-side count
+    const int blocks = sm_count * RT1W_GRID_PER_SM;
     size_t perlin_bytes = size_t(args.sc.n_perlins) * sizeof(DPerlin);
     const int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
     if (!perlin_in_smem) perlin_bytes = 0;
@@ -463,35 +442,24 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     uint64_t wave = 0;
     for (;;) {
         for (int k = 0; k < poll_every; ++k, ++wave) {
-            const int parity = int(wave & 1);
-            mark(K_GENERATE);
-            k_generate<<<gen_blocks, kGenThreads, 0, stream>>>(args, parity);
-            mark(K_EXTEND);
-            if (flat && media) k_extend<true, true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
-            else if (flat) k_extend<true, false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
-            else if (media) k_extend<false, true><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
-            else k_extend<false, false><<<ext_blocks, kExtendThreads, 0, stream>>>(args, parity);
-            ws.launches += 2;
-#define RT1W_SHADE(MAT, SMEM, PSM)                                                                                                                    \
-    if (material_mask & (1 << MAT)) {                                                                                                                 \
-        mark(K_SHADE0 + MAT);                                                                                                                         \
-        launch_shade<MAT>(args, parity, shade_blocks, SMEM, PSM, stream);                                                                             \
-        ++ws.launches;                                                                                                                                \
-    }
-            RT1W_SHADE(RT1W_MAT_LAMBERTIAN, perlin_bytes, perlin_in_smem)
-            RT1W_SHADE(RT1W_MAT_METAL, 0, 0)
-            RT1W_SHADE(RT1W_MAT_DIELECTRIC, 0, 0)
-            RT1W_SHADE(RT1W_MAT_ISOTROPIC, perlin_bytes, perlin_in_smem)
-            RT1W_SHADE(RT1W_MAT_DIFFUSE_LIGHT, perlin_bytes, perlin_in_smem)
-#undef RT1W_SHADE
+            const int slot = int(wave % 3), parity = int(wave & 1);
+            mark(K_WAVE);
+            if (flat && media) k_wave<true, true><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            else if (flat) k_wave<true, false><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            else if (media) k_wave<false, true><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            else k_wave<false, false><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            ++ws.launches;
         }
         mark(-1);
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(h_ctr, args.pool.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) break;
         if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) break;
         drain_marks();
-        // after wave (wave-1): continuing rays sit in ext[wave & 1], and next_path[wave & 1] is what wave `wave` would see
-        if (h_ctr->next_path[wave & 1] >= args.rp.total_paths && h_ctr->n_ext[wave & 1] == 0) break;
+        // what wave `wave` would see: no path left to start and no hit queued
+        const int slot = int(wave % 3);
+        uint32_t queued = 0;
+        for (int q = 0; q < Q_COUNT; ++q) queued += h_ctr->n_mat[slot][q];
+        if (h_ctr->next_path[slot] >= args.rp.total_paths && queued == 0) break;
     }
     for (auto &m : marks) cudaEventDestroy(m.ev);
     for (auto ev : spare) cudaEventDestroy(ev);

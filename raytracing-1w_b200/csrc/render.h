@@ -10,12 +10,12 @@
 
 namespace rt1w {
 
-// Device-side counters of the wavefront queues (one struct per context, zeroed per render).
+// Device-side counters of the wavefront queues (one struct per context, zeroed per render).  Three copies
+// rotate: wave w reads slot w % 3, appends to slot (w + 1) % 3 and clears slot (w + 2) % 3 for wave w + 1.
 struct Counters {
-    uint32_t n_ext[2];            // rays that shade kernels of wave w-1 appended to the extend queue of wave w (index w & 1)
-    uint32_t n_mat[Q_COUNT];      // hits queued per material family (rt1w_material_type) for the shade kernels of the current wave
+    uint32_t n_mat[3][Q_COUNT];      // hits queued per material family (rt1w_material_type) for the wave that reads the slot
     uint32_t pad;
-    unsigned long long next_path[2]; // next (pixel, sample) pair to start, as seen by wave w (index w & 1)
+    unsigned long long next_path[3]; // next (pixel, sample) pair to start, as seen by the wave that reads the slot
     unsigned long long rays;         // closest-hit queries so far
 };
 
@@ -26,14 +26,13 @@ struct RayQueue {
     RayB *b = nullptr;    // origin.z, direction.x, direction.y
     RayC *c = nullptr;    // direction.z, time, state, pixel
     float4 *t = nullptr;  // throughput rgb (+ unused lane)
-    HitRec *h = nullptr;  // material queues only: t, leaf, meta
+    HitRec *h = nullptr;  // t, leaf, meta of the hit the ray ended on
 };
 
-// The queues of a render: two extend queues (ping-pong between waves) and one hit queue per material.
+// The queues of a render: one hit queue per scattering material family, double-buffered between waves.
 // No path owns a slot: rays move from queue to queue, compacted at every stage.
 struct Pool {
-    RayQueue ext[2];
-    RayQueue mat[Q_COUNT];
+    RayQueue mat[2][Q_COUNT];
     Counters *ctr = nullptr;
     uint32_t capacity = 0;  // rays in flight per wave (<= allocated)
     uint32_t allocated = 0; // entries every queue was allocated with
@@ -52,7 +51,7 @@ struct RenderArgs {
     float *stat;  // width*height*6 clamped sum / sum of squares, or nullptr
 };
 
-enum KernelSlot : int { K_GENERATE = 0, K_EXTEND = 1, K_SHADE0 = 2, K_COUNT = 2 + Q_COUNT }; // K_SHADE0 + rt1w_material_type
+enum KernelSlot : int { K_WAVE = 0, K_FINISH = 1, K_COUNT = RT1W_KERNEL_COUNT };
 
 struct WaveStats {
     uint64_t waves = 0, launches = 0, rays = 0;

@@ -9,5 +9,5 @@ import json
 d=json.loads(open('gpurun_out/${TAG}_bench.json').read().strip().splitlines()[-1])
 print('Mpaths/s',round(d['value'],1),'ms/step',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1), {k:v['ms'] for k,v in d['kernels'].items()})"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_generate|k_extend|k_shade" -s ${2:-14} -c 7 -o gpurun_out/${TAG}_wave $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_wave|k_finish" -s ${2:-5} -c 3 -o gpurun_out/${TAG}_wave $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out | grep ${TAG}

@@ -227,7 +227,13 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
             const rt1w_flat_prim &fp = low.prims[bvh.prim_order[leaf]];
             return fp.kind == RT1W_NODE_MOVING_SPHERE ? -1 : fp.frame;
         };
-        std::stable_sort(scan.begin(), scan.end(), [&](int a, int b) { return box_frame(a) < box_frame(b); });
+        auto is_sphere = [&](int leaf) { // plain spheres get an f32 discriminant screen (kernels.cuh: flat_is_sphere)
+            const rt1w_flat_prim &fp = low.prims[bvh.prim_order[leaf]];
+            return fp.kind == RT1W_NODE_SPHERE ? 1 : 0;
+        };
+        std::stable_sort(scan.begin(), scan.end(), [&](int a, int b) {
+            return box_frame(a) != box_frame(b) ? box_frame(a) < box_frame(b) : is_sphere(a) < is_sphere(b);
+        });
         for (size_t k = 0; k < n; ++k) {
             const rt1w_flat_prim &fp = low.prims[bvh.prim_order[scan[k]]];
             const int bf = box_frame(scan[k]);

@@ -106,7 +106,7 @@ struct FrameXf {
 };
 static_assert(offsetof(DFrame, bz) == 32, "FrameXf must alias the head of DFrame");
 
-RT1W_DEV const FrameXf *frame_xf(const SceneView &sc, int frame) { return reinterpret_cast<const FrameXf *>(sc.frames + frame); }
+RT1W_DEV const FrameXf *frame_xf(const DFrame *frames, int frame) { return reinterpret_cast<const FrameXf *>(frames + frame); }
 
 RT1W_DEV LocalRay to_local(const FrameXf *f, const Ray &r) { // f == nullptr: no wrapper chain
     LocalRay l;
@@ -206,16 +206,16 @@ RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, d
 
 // One candidate primitive (record at `P`: global memory, or the shared-memory copy of the flat-scan
 // path).  Returns true and the hit parameter when it lands in [t_min, tmax].
-// `flat_frames`: shared-memory copies of the wrapper frames (flat scan) or nullptr (read them from global memory).
+// `frames`: the wrapper frames (global memory, or the flat scan's shared-memory copies).
 // MEDIA = false compiles the ConstantMedium cases out (scenes without media: no Philox, no f64 slabs in the loop).
 template <bool EXACT, bool MEDIA>
-RT1W_DEV bool hit_prim(const SceneView &sc, const FrameXf *flat_frames, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
+RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
     const double2 *w = reinterpret_cast<const double2 *>(P);
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3); // q2 | meta | frame
     const uint32_t meta = uint32_t(tail.z);
     const int type = int(meta & 15u);
     const double2 p01 = w[0], p23 = w[1];
-    const LocalRay l = to_local(tail.w < 0 ? nullptr : (flat_frames ? flat_frames + tail.w : frame_xf(sc, tail.w)), r);
+    const LocalRay l = to_local(tail.w < 0 ? nullptr : frame_xf(frames, tail.w), r);
     switch (type) {
     case P_SPHERE: return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
     case P_MOVING_SPHERE: { // moving_sphere.rs:23-26,31-48
@@ -339,7 +339,7 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
         const uint32_t first = ref & 0x1fffffffu, count = ref >> 29;
         for (uint32_t i = 0; i < count; ++i) {
             double t;
-            if (hit_prim<EXACT, MEDIA>(sc, nullptr, sc.prims + (first + i), int(first + i), r, best, mr, t)) {
+            if (hit_prim<EXACT, MEDIA>(sc, sc.frames, sc.prims + (first + i), int(first + i), r, best, mr, t)) {
                 best = t, best_leaf = int(first + i);
                 bestf = __double2float_ru(t);
             }
@@ -366,24 +366,41 @@ constexpr int kFlatMaxFrames = 8;
 struct FlatScene {
     DPrim prims[kFlatMax];             // leaf order
     float4 lo[kFlatMax], hi[kFlatMax]; // scan order: padded f32 bounds in the frame of the group; lo.w = leaf (int bits)
-    FrameXf frames[kFlatMaxFrames];
-    int32_t group_end[kFlatMaxFrames + 1]; // scan-order groups: group g = boxes [group_end[g-1], group_end[g]) in ...
-    int32_t group_frame[kFlatMaxFrames + 1]; // ... frame group_frame[g] (-1 = world)
+    float4 sphere[kFlatMax];           // scan order, sphere groups: centre and radius in f32
+    DFrame frames[kFlatMaxFrames];
+    // scan-order groups: group g = boxes [group_end[g-1], group_end[g]) in frame group_frame[g] (-1 = world);
+    // group_sphere[g]: plain spheres, screened by an f32 discriminant on top of the box
+    int32_t group_end[2 * kFlatMaxFrames + 2];
+    int32_t group_frame[2 * kFlatMaxFrames + 2];
+    int32_t group_sphere[2 * kFlatMaxFrames + 2];
     int32_t n_groups;
+    uint32_t skip_bit[kFlatMax]; // leaf -> scan bit of a rectangle (a ray leaving a rectangle cannot hit it again), else 0
 };
+
+// scan-order sort key shared with the host (api.cu lists the boxes in this order)
+RT1W_DEV bool flat_is_sphere(const DPrim &p, int box_frame) { return int(p.meta & 15u) == P_SPHERE && box_frame == p.frame; }
 
 RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the whole CTA, then __syncthreads()
     const int n = sc.n_prims;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(sc.prims);
     uint32_t *dst = reinterpret_cast<uint32_t *>(fs.prims);
     for (int w = threadIdx.x; w < n * int(sizeof(DPrim) / 4); w += blockDim.x) dst[w] = src[w];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) fs.lo[i] = sc.prim_boxes[2 * i], fs.hi[i] = sc.prim_boxes[2 * i + 1];
-    for (int i = threadIdx.x; i < sc.n_frames; i += blockDim.x) fs.frames[i] = *frame_xf(sc, i);
-    if (threadIdx.x == 0) { // the host lists the boxes frame by frame (hi.w = frame of the box)
+    src = reinterpret_cast<const uint32_t *>(sc.frames), dst = reinterpret_cast<uint32_t *>(fs.frames);
+    for (int w = threadIdx.x; w < sc.n_frames * int(sizeof(DFrame) / 4); w += blockDim.x) dst[w] = src[w];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float4 lo = sc.prim_boxes[2 * i], hi = sc.prim_boxes[2 * i + 1];
+        fs.lo[i] = lo, fs.hi[i] = hi;
+        const DPrim &p = sc.prims[__float_as_int(lo.w)];
+        fs.sphere[i] = make_float4(float(p.p[0]), float(p.p[1]), float(p.p[2]), float(p.p[3]));
+        const int type = int(p.meta & 15u);
+        fs.skip_bit[__float_as_int(lo.w)] = (type == P_XY_RECT || type == P_XZ_RECT || type == P_YZ_RECT) ? 1u << i : 0u;
+    }
+    if (threadIdx.x == 0) { // the host lists the boxes frame by frame, plain spheres last within a frame (hi.w = frame of the box)
         int g = 0;
         for (int i = 0; i < n; ++i) {
             const int frame = __float_as_int(sc.prim_boxes[2 * i + 1].w);
-            if (i == 0 || frame != fs.group_frame[g - 1]) fs.group_frame[g++] = frame;
+            const int sph = flat_is_sphere(sc.prims[__float_as_int(sc.prim_boxes[2 * i].w)], frame) ? 1 : 0;
+            if (i == 0 || frame != fs.group_frame[g - 1] || sph != fs.group_sphere[g - 1]) fs.group_frame[g] = frame, fs.group_sphere[g] = sph, ++g;
             fs.group_end[g - 1] = i + 1;
         }
         fs.n_groups = g;
@@ -418,30 +435,59 @@ RT1W_DEV bool slab_fma(const float4 lo, const float4 hi, const SlabRayF &s, floa
     return tnear <= tf;
 }
 
+// f32 screen of a plain sphere on top of its box: false only when the ray certainly misses it beyond t_min
+// (discriminant below its rounding bound, or sphere behind an origin outside it).
+RT1W_DEV bool sphere_maybe(const float4 sp, f3 o, f3 d) {
+    const f3 oc = mk3(o.x - sp.x, o.y - sp.y, o.z - sp.z);
+    const float a = dot(d, d), hb = dot(oc, d), oc2 = dot(oc, oc), r2 = sp.w * sp.w;
+    const float cc = oc2 - r2, scale = oc2 + r2;
+    const float disc = hb * hb - a * cc;
+    if (disc < -4e-6f * (hb * hb + a * scale)) return false;
+    return !(cc > 4e-6f * scale && hb > 0.0f);
+}
+
 // `tn_col`: this thread's column of the CTA's entry-distance table (stride = blockDim.x floats).
+// `skip_leaf`: the rectangle the ray starts on (its only root is t ~ 0 < t_min), or -1.
 template <bool EXACT, bool MEDIA>
 RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const Ray &r, const MediumRng &mr, float *tn_col, int stride,
-                               double &t_best, int &leaf_best) {
+                               int skip_leaf, double &t_best, int &leaf_best) {
     uint32_t cand = 0, bit = 1;
+    const uint32_t keep = ~(skip_leaf >= 0 ? fs.skip_bit[skip_leaf] : 0u);
     float t1 = CUDART_INF_F;
     int k1 = -1;
     const int n_groups = fs.n_groups;
-    int k = 0;
+    int k = 0, cur_frame = -2;
+    SlabRayF s;
+    f3 o, d;
     for (int g = 0; g < n_groups; ++g) {
         const int frame = fs.group_frame[g], end = fs.group_end[g];
-        SlabRayF s;
-        if (frame < 0) {
-            s = slab_ray(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
-        } else {
-            const LocalRay l = to_local(fs.frames + frame, r);
-            s = slab_ray(l.ox, l.oy, l.oz, float(l.dx), float(l.dy), float(l.dz));
+        if (frame != cur_frame) {
+            cur_frame = frame;
+            if (frame < 0) {
+                s = slab_ray(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
+                o = mk3(float(r.ox), float(r.oy), float(r.oz)), d = mk3(r.dx, r.dy, r.dz);
+            } else {
+                const LocalRay l = to_local(frame_xf(fs.frames, frame), r);
+                s = slab_ray(l.ox, l.oy, l.oz, float(l.dx), float(l.dy), float(l.dz));
+                o = mk3(float(l.ox), float(l.oy), float(l.oz)), d = mk3(float(l.dx), float(l.dy), float(l.dz));
+            }
         }
-        for (; k < end; ++k, bit <<= 1) {
-            float tn;
-            const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn);
-            tn_col[k * stride] = tn;
-            if (in) cand |= bit;
-            if (in && tn < t1) t1 = tn, k1 = k;
+        if (fs.group_sphere[g]) {
+            for (; k < end; ++k, bit <<= 1) {
+                float tn;
+                const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn) && sphere_maybe(fs.sphere[k], o, d);
+                tn_col[k * stride] = tn;
+                if (in) cand |= bit;
+                if (in && tn < t1) t1 = tn, k1 = k;
+            }
+        } else {
+            for (; k < end; ++k, bit <<= 1) {
+                float tn;
+                const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn) && (bit & keep) != 0u;
+                tn_col[k * stride] = tn;
+                if (in) cand |= bit;
+                if (in && tn < t1) t1 = tn, k1 = k;
+            }
         }
     }
     double best = CUDART_INF;
@@ -491,10 +537,11 @@ RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
     u = phi * (0.5f / kPiF), v = theta * (1.0f / kPiF);
 }
 
-template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const SceneView &sc, int leaf, const Ray &r, double t) {
+// P: the primitive's record, frames: the wrapper frames (global memory or the flat scan's shared-memory copies).
+template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const DPrim *P, const DFrame *frames, const Ray &r, double t) {
     HitInfo h;
-    const double2 *w = reinterpret_cast<const double2 *>(sc.prims + leaf);
-    const int4 tail = __ldg(reinterpret_cast<const int4 *>(w + 3));
+    const double2 *w = reinterpret_cast<const double2 *>(P);
+    const int4 tail = *reinterpret_cast<const int4 *>(w + 3);
     h.meta = uint32_t(tail.z);
     h.type = int(h.meta & 15u);
     const int frame = tail.w;
@@ -504,61 +551,72 @@ template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const SceneView &sc, int l
     if (h.type == P_MEDIUM_SPHERE || h.type == P_MEDIUM_BOX) { // constant_medium.rs:104-112
         h.normal = h.n_out = mk3(1.0f, 0.0f, 0.0f);
         h.front_face = true;
-    } else {
-        const LocalRay l = to_local(frame < 0 ? nullptr : frame_xf(sc, frame), r);
-        const double lx = l.ox + t * l.dx, ly = l.oy + t * l.dy, lz = l.oz + t * l.dz;
-        const double2 p01 = __ldg(w), p23 = __ldg(w + 1);
-        f3 n;
-        if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
-            double cx = p01.x, cy = p01.y, cz = p23.x;
-            if (h.type == P_MOVING_SPHERE) {
-                const float4 f = __ldg(reinterpret_cast<const float4 *>(w + 2));
-                const double s = double((r.time - f.w) * __int_as_float(tail.x));
-                cx += s * double(f.x), cy += s * double(f.y), cz += s * double(f.z);
-            }
-            const double inv_r = 1.0 / p23.y; // sphere.rs:51
-            n = mk3(float((lx - cx) * inv_r), float((ly - cy) * inv_r), float((lz - cz) * inv_r));
-            if (WANT_UV) sphere_uv(n, h.u, h.v);
-        } else {
-            double a, b;
-            if (h.type == P_XY_RECT) n = mk3(0.0f, 0.0f, 1.0f), a = lx, b = ly;
-            else if (h.type == P_XZ_RECT) n = mk3(0.0f, 1.0f, 0.0f), a = lx, b = lz;
-            else n = mk3(1.0f, 0.0f, 0.0f), a = ly, b = lz;
-            if (WANT_UV) { // aarect.rs:60-61
-                h.u = float((a - p01.x) / (p01.y - p01.x));
-                h.v = float((b - p23.x) / (p23.y - p23.x));
-            }
-        }
-        h.n_out = n;
-        // HitRecord::new at the leaf, with the leaf-space ray (hittable.rs:30-35)
-        bool ff = (l.dx * double(n.x) + l.dy * double(n.y) + l.dz * double(n.z)) < 0.0;
-        if (!ff) n = -n;
-        if (frame >= 0) {
-            const DFrame *f = sc.frames + frame;
-            const int n_ops = f->n_ops;
-            for (int i = 0; i < n_ops; ++i) { // innermost wrapper first
-                const DChainOp op = f->ops[i];
-                if (op.kind == OP_FLIP_FACE) { // hittable.rs:290-294
-                    ff = !ff;
-                    continue;
-                }
-                if (op.kind == OP_ROTATE_Y) { // hittable.rs:263-267
-                    const float nx = op.cos_own * n.x + op.sin_own * n.z;
-                    const float nz = -op.sin_own * n.x + op.cos_own * n.z;
-                    n.x = nx, n.z = nz;
-                }
-                // both wrappers re-run HitRecord::new with the ray INSIDE the wrapper (hittable.rs:221-229,269-277)
-                const float dx = op.cos_cum * r.dx - op.sin_cum * r.dz;
-                const float dz = op.sin_cum * r.dx + op.cos_cum * r.dz;
-                ff = (dx * n.x + r.dy * n.y + dz * n.z) < 0.0f;
-                if (!ff) n = -n;
-            }
-        } else if ((h.meta >> 4) & PF_FLIP_FACE) {
-            ff = !ff;
-        }
-        h.normal = n;
-        h.front_face = ff;
+        return h;
     }
+    f3 n, ld; // outward normal and ray direction in the leaf's own space
+    double lx, ly, lz; // hit point in the leaf's own space
+    if (frame < 0) {
+        ld = mk3(r.dx, r.dy, r.dz);
+        lx = h.px, ly = h.py, lz = h.pz;
+    } else { // hittable.rs:207,241-245
+        const FrameXf *f = frame_xf(frames, frame);
+        const double s = f->sin_t, c = f->cos_t;
+        ld = mk3(float(c * double(r.dx) - s * double(r.dz)), r.dy, float(s * double(r.dx) + c * double(r.dz)));
+        lx = c * h.px - s * h.pz + f->bx, ly = h.py + f->by, lz = s * h.px + c * h.pz + f->bz;
+    }
+    bool ff;
+    if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
+        const double2 p01 = w[0], p23 = w[1];
+        double cx = p01.x, cy = p01.y, cz = p23.x;
+        if (h.type == P_MOVING_SPHERE) {
+            const float4 f = *reinterpret_cast<const float4 *>(w + 2);
+            const double s = double((r.time - f.w) * __int_as_float(tail.x));
+            cx += s * double(f.x), cy += s * double(f.y), cz += s * double(f.z);
+        }
+        const float inv_r = 1.0f / float(p23.y); // sphere.rs:51
+        n = mk3(float(lx - cx) * inv_r, float(ly - cy) * inv_r, float(lz - cz) * inv_r);
+        if (WANT_UV) sphere_uv(n, h.u, h.v);
+        ff = dot(ld, n) < 0.0f; // HitRecord::new at the leaf, with the leaf-space ray (hittable.rs:30-35)
+    } else {
+        float dn;
+        if (h.type == P_XY_RECT) n = mk3(0.0f, 0.0f, 1.0f), dn = ld.z;
+        else if (h.type == P_XZ_RECT) n = mk3(0.0f, 1.0f, 0.0f), dn = ld.y;
+        else n = mk3(1.0f, 0.0f, 0.0f), dn = ld.x;
+        if (WANT_UV) { // aarect.rs:60-61
+            const double2 p01 = w[0], p23 = w[1];
+            const double a = h.type == P_YZ_RECT ? ly : lx, b = h.type == P_XY_RECT ? ly : lz;
+            h.u = float((a - p01.x) / (p01.y - p01.x));
+            h.v = float((b - p23.x) / (p23.y - p23.x));
+        }
+        ff = dn < 0.0f;
+    }
+    h.n_out = n;
+    if (!ff) n = -n;
+    if (frame >= 0) {
+        const DFrame *f = frames + frame;
+        const int n_ops = f->n_ops;
+        for (int i = 0; i < n_ops; ++i) { // innermost wrapper first
+            const DChainOp op = f->ops[i];
+            if (op.kind == OP_FLIP_FACE) { // hittable.rs:290-294
+                ff = !ff;
+                continue;
+            }
+            if (op.kind == OP_ROTATE_Y) { // hittable.rs:263-267
+                const float nx = op.cos_own * n.x + op.sin_own * n.z;
+                const float nz = -op.sin_own * n.x + op.cos_own * n.z;
+                n.x = nx, n.z = nz;
+            }
+            // both wrappers re-run HitRecord::new with the ray INSIDE the wrapper (hittable.rs:221-229,269-277)
+            const float dx = op.cos_cum * r.dx - op.sin_cum * r.dz;
+            const float dz = op.sin_cum * r.dx + op.cos_cum * r.dz;
+            ff = (dx * n.x + r.dy * n.y + dz * n.z) < 0.0f;
+            if (!ff) n = -n;
+        }
+    } else if ((h.meta >> 4) & PF_FLIP_FACE) {
+        ff = !ff;
+    }
+    h.normal = n;
+    h.front_face = ff;
     return h;
 }
 

@@ -157,10 +157,12 @@ RT1W_DEV Ray generate_ray(const RenderArgs &a, unsigned long long k, uint32_t &s
 // scattered ray, advances the depth in c.state and folds the attenuation into `thr`.  Returns false when
 // the path ends here (depth limit, main.rs:59-61).
 // ------------------------------------------------------------------------------------------
+// `prims`, `frames`: the scene tables (global memory, or the flat scan's shared-memory copies).
 template <int MAT>
-RT1W_DEV bool scatter(const RenderArgs &a, const DPerlin *perlins, const DLight *lights, Ray &r, const HitRec &hr, RayC &c, f3 &thr) {
+RT1W_DEV bool scatter(const RenderArgs &a, const DPrim *prims, const DFrame *frames, const DPerlin *perlins, const DLight *lights, Ray &r,
+                      const HitRec &hr, RayC &c, f3 &thr) {
     const DMaterial m = a.sc.materials[hr.meta >> 12];
-    const HitInfo h = finalize_hit<false>(a.sc, hr.leaf, r, hr.t);
+    const HitInfo h = finalize_hit<false>(prims + hr.leaf, frames, r, hr.t);
     const uint32_t depth = c.state & 255u;
     Rng rng;
     path_rng_key(a.rp, c.pixel, rng.k0, rng.k1);
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
     for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
     __syncthreads();
 
+    const DPrim *prims = FLAT ? s_flat[0].prims : a.sc.prims;
+    const DFrame *frames = FLAT ? s_flat[0].frames : a.sc.frames;
     const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
     uint32_t traced = 0;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
         RayC c;
         f3 thr;
         bool alive = false;
+        int skip_leaf = -1; // the primitive the ray starts on
         if (i < off4) { // a hit queued by the previous wave: scatter
             const int seg = i < off1 ? 0 : (i < off2 ? 1 : (i < off3 ? 2 : 3)); // warp-uniform
             const uint32_t j = i - (seg == 0 ? 0u : (seg == 1 ? off1 : (seg == 2 ? off2 : off3)));
@@ -259,12 +264,13 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
                 const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
                 r = load_ray(in, j, c);
                 const HitRec hr = in.h[j];
+                skip_leaf = hr.leaf;
                 const float4 th4 = in.t[j];
                 thr = mk3(th4.x, th4.y, th4.z);
-                if (seg == 0) alive = scatter<RT1W_MAT_LAMBERTIAN>(a, perlins, s_lights, r, hr, c, thr);
-                else if (seg == 1) alive = scatter<RT1W_MAT_METAL>(a, perlins, s_lights, r, hr, c, thr);
-                else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, perlins, s_lights, r, hr, c, thr);
-                else alive = scatter<RT1W_MAT_ISOTROPIC>(a, perlins, s_lights, r, hr, c, thr);
+                if (seg == 0) alive = scatter<RT1W_MAT_LAMBERTIAN>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
+                else if (seg == 1) alive = scatter<RT1W_MAT_METAL>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
+                else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
+                else alive = scatter<RT1W_MAT_ISOTROPIC>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
             }
         } else if (i < total) { // a new camera path
             r = generate_ray(a, path0 + (i - off4), c.state, c.pixel);
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
-            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kWaveThreads, h.t, h.leaf)
+            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kWaveThreads, skip_leaf, h.t, h.leaf)
                                   : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
             int mat_type = RT1W_MAT_NONE;
             if (hit) {
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
                 mat_type = int((h.meta >> 8) & 15u);
             }
             if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
-                const HitInfo hi = finalize_hit<false>(a.sc, h.leaf, r, h.t);
+                const HitInfo hi = finalize_hit<false>(prims + h.leaf, frames, r, h.t);
                 const f3 e = hi.front_face ? texture_value(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
                 splat(a, c.pixel, thr, e);
             } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
@@ -345,10 +351,10 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
         mr.c0 = uint32_t(i), mr.c1 = uint32_t(uint64_t(i) >> 32), mr.c2 = RNG_TRACE_MEDIUM, mr.k0 = seed_lo, mr.k1 = seed_hi;
         double t;
         int leaf;
-        const bool hit = flat ? closest_hit_flat<true, true>(sc, s_flat, r, mr, s_tn + threadIdx.x, kExtendThreads, t, leaf)
+        const bool hit = flat ? closest_hit_flat<true, true>(sc, s_flat, r, mr, s_tn + threadIdx.x, kExtendThreads, -1, t, leaf)
                               : closest_hit<true, true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
         HitInfo h;
-        if (hit) h = finalize_hit<true>(sc, leaf, r, t);
+        if (hit) h = finalize_hit<true>(sc.prims + leaf, sc.frames, r, t);
         if (prim_id) prim_id[i] = hit ? sc.prim_id[leaf] : -1;
         if (t_out) t_out[i] = hit ? float(t) : CUDART_INF_F;
         if (normal3) {

@@ -23,6 +23,11 @@
 namespace rt1w {
 
 #define RT1W_DEV __device__ __forceinline__
+#ifdef RT1W_OUTLINE_SHADE // experiment: one copy of the big shading helpers instead of one per material
+#define RT1W_DEV_BIG static __device__ __noinline__
+#else
+#define RT1W_DEV_BIG __device__ __forceinline__
+#endif
 
 constexpr double kTMin = 0.001;      // main.rs:62
 constexpr float kPiF = 3.14159265358979323846f;
@@ -538,7 +543,7 @@ RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
 }
 
 // P: the primitive's record, frames: the wrapper frames (global memory or the flat scan's shared-memory copies).
-template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const DPrim *P, const DFrame *frames, const Ray &r, double t) {
+template <bool WANT_UV> RT1W_DEV_BIG HitInfo finalize_hit(const DPrim *P, const DFrame *frames, const Ray &r, double t) {
     HitInfo h;
     const double2 *w = reinterpret_cast<const double2 *>(P);
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3);
@@ -661,7 +666,7 @@ RT1W_DEV float sin_reduced(double x) {
 }
 
 // `perlins` may point at shared memory copies of the tables (render.cu stages them per CTA).
-RT1W_DEV f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
+RT1W_DEV_BIG f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
     DTexture t = sc.textures[tex];
     for (int guard = 0; guard < 9 && t.type == RT1W_TEX_CHECKER; ++guard) { // texture.rs:46-55
         const float sines = sin_reduced(10.0 * h.px) * sin_reduced(10.0 * h.py) * sin_reduced(10.0 * h.pz);

@@ -33,7 +33,7 @@ namespace rt1w {
 #define RT1W_WAVE_THREADS 128
 #endif
 #ifndef RT1W_FLAT_MIN_BLOCKS
-#define RT1W_FLAT_MIN_BLOCKS 4
+#define RT1W_FLAT_MIN_BLOCKS 5
 #endif
 #ifndef RT1W_BVH_MIN_BLOCKS
 #define RT1W_BVH_MIN_BLOCKS 4
@@ -201,7 +201,11 @@ RT1W_DEV bool scatter(const RenderArgs &a, const DPrim *prims, const DFrame *fra
 // FLAT: scan the primitive list staged in shared memory (small scenes) instead of walking the BVH.
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 template <bool FLAT, bool MEDIA>
+#ifdef RT1W_REGS_FROM_FLAG // sweeps: register budget from --maxrregcount instead of the launch bounds
+__global__ void
+#else
 __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS)
+#endif
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
     // one static buffer: the staged primitive list + entry-distance table (FLAT) or the per-thread traversal stacks (BVH)
@@ -410,14 +414,19 @@ void pool_free(Pool &pool) {
 cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_ctr, cudaStream_t stream, int sm_count, WaveStats &ws) {
     cudaError_t e = cudaMemsetAsync(args.pool.ctr, 0, sizeof(Counters), stream);
     if (e != cudaSuccess) return e;
-    // grid: a fixed multiple of the SM count; the kernel grid-strides over a device-side count
-    const int blocks = sm_count * RT1W_GRID_PER_SM;
+    const bool flat = args.sc.flat != 0;
+    const bool media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
     size_t perlin_bytes = size_t(args.sc.n_perlins) * sizeof(DPerlin);
     const int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
     if (!perlin_in_smem) perlin_bytes = 0;
     const int poll_every = 8;
-    const bool flat = args.sc.flat != 0;
-    const bool media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
+    // grid: every CTA resident at once (SM count x occupancy); the kernel grid-strides over a device-side count
+    using WaveKernel = void (*)(const RenderArgs, const int, const int, const int);
+    const WaveKernel kernel = flat ? (media ? k_wave<true, true> : k_wave<true, false>) : (media ? k_wave<false, true> : k_wave<false, false>);
+    if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWaveThreads, perlin_bytes)) != cudaSuccess) return e;
+    const int blocks = sm_count * (per_sm > 0 ? per_sm : 1);
 
     // profiling mode: one event before every launch and one at the end of the chunk
     struct Mark {
@@ -450,10 +459,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         for (int k = 0; k < poll_every; ++k, ++wave) {
             const int slot = int(wave % 3), parity = int(wave & 1);
             mark(K_WAVE);
-            if (flat && media) k_wave<true, true><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
-            else if (flat) k_wave<true, false><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
-            else if (media) k_wave<false, true><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
-            else k_wave<false, false><<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            kernel<<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
             ++ws.launches;
         }
         mark(-1);

@@ -50,6 +50,9 @@ void local_bounds(const rt1w_flat_prim &fp, double lo[3], double hi[3]) {
         lo[a] = p[0], hi[a] = p[1], lo[b] = p[2], hi[b] = p[3], lo[ax] = p[4] - 0.0001, hi[ax] = p[4] + 0.0001;
         break;
     }
+    case RT1W_NODE_AABOX: // merged box: p = min xyz, max xyz
+        for (int c = 0; c < 3; ++c) lo[c] = p[c], hi[c] = p[3 + c];
+        break;
     case RT1W_NODE_CONSTANT_MEDIUM:
         if (fp.boundary != RT1W_NODE_SPHERE) { // p = min xyz, -1/density, max xyz
             for (int c = 0; c < 3; ++c) lo[c] = p[c], hi[c] = p[4 + c];
@@ -184,11 +187,41 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     rt1w_status st = lower_scene(desc, low, err);
     if (st != RT1W_OK) return fail(st, err);
 
-    const size_t n = low.prims.size();
+    // Device primitives: the lowered primitives, except that the six rectangles of an AABox (aabox.rs:29-76) travel
+    // as ONE box primitive (kernels.cuh: hit_box); hits still name the rectangle (first id + side).
+    std::vector<rt1w_flat_prim> dev;
+    std::vector<int32_t> dev_first_id;
+    // scenes small enough for the flat scan keep their rectangles: the scan's frame-local boxes already cull five of a
+    // box's six sides, and one code path for walls and box sides beats the shorter list (measured, Cornell box)
+    const bool merge_boxes = low.prims.size() > size_t(kFlatMax) || low.frames.size() > size_t(kFlatMaxFrames);
+    for (size_t i = 0; i < low.prims.size();) {
+        const rt1w_flat_prim &f0 = low.prims[i];
+        bool is_box = merge_boxes && f0.kind == RT1W_NODE_XY_RECT && f0.node >= 0 && f0.node < desc->n_nodes && desc->nodes[f0.node].type == RT1W_NODE_AABOX &&
+                      i + 6 <= low.prims.size();
+        for (size_t k = 1; is_box && k < 6; ++k) is_box = low.prims[i + k].node == f0.node && low.prims[i + k].frame == f0.frame;
+        if (!is_box) {
+            dev.push_back(f0), dev_first_id.push_back(int32_t(i));
+            ++i;
+            continue;
+        }
+        rt1w_flat_prim b = f0; // sides: XY@z1, XY@z0, XZ@y1, ... with p = a0, a1, b0, b1, k
+        b.kind = RT1W_NODE_AABOX;
+        b.p[0] = f0.p[0], b.p[1] = f0.p[2], b.p[2] = low.prims[i + 1].p[4]; // x0, y0, z0
+        b.p[3] = f0.p[1], b.p[4] = f0.p[3], b.p[5] = f0.p[4];               // x1, y1, z1
+        for (size_t k = 1; k < 6; ++k)
+            for (int c = 0; c < 3; ++c) {
+                b.bbox_min[c] = std::min(b.bbox_min[c], low.prims[i + k].bbox_min[c]);
+                b.bbox_max[c] = std::max(b.bbox_max[c], low.prims[i + k].bbox_max[c]);
+            }
+        dev.push_back(b), dev_first_id.push_back(int32_t(i));
+        i += 6;
+    }
+    const size_t n = dev.size();
+    if (n >= size_t(1) << kLeafBits) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^28 primitives");
     std::vector<double> bmin(3 * n), bmax(3 * n);
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) {
-            bmin[3 * i + k] = low.prims[i].bbox_min[k], bmax[3 * i + k] = low.prims[i].bbox_max[k];
+            bmin[3 * i + k] = dev[i].bbox_min[k], bmax[3 * i + k] = dev[i].bbox_max[k];
             if (!std::isfinite(bmin[3 * i + k]) || !std::isfinite(bmax[3 * i + k]))
                 return fail(RT1W_ERR_INVALID, "No bounding box in bvh_node constructor. (bvh.rs:65-67): non-finite primitive bounds");
         }
@@ -198,9 +231,9 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     std::vector<DPrim> dprims(n);
     std::vector<int32_t> prim_id(n);
     for (size_t i = 0; i < n; ++i) {
-        const rt1w_flat_prim &fp = low.prims[bvh.prim_order[i]];
+        const rt1w_flat_prim &fp = dev[bvh.prim_order[i]];
         dprims[i] = make_device_prim(fp, low.materials);
-        prim_id[i] = int32_t(bvh.prim_order[i]);
+        prim_id[i] = dev_first_id[bvh.prim_order[i]];
     }
     // Small scenes are scanned, not traversed (kernels.cuh: closest_hit_flat): one padded f32 box per primitive in
     // the primitive's own frame, listed frame by frame; lo.w = leaf index, hi.w = frame of the BOX (-1 = world).
@@ -213,9 +246,9 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
         double reach = 0.0;
         for (size_t i = 0; i < n; ++i) {
             double llo[3], lhi[3];
-            local_bounds(low.prims[i], llo, lhi);
+            local_bounds(dev[i], llo, lhi);
             for (int c = 0; c < 3; ++c) {
-                reach = std::max(reach, std::max(std::fabs(low.prims[i].bbox_min[c]), std::fabs(low.prims[i].bbox_max[c])));
+                reach = std::max(reach, std::max(std::fabs(dev[i].bbox_min[c]), std::fabs(dev[i].bbox_max[c])));
                 reach = std::max(reach, std::max(std::fabs(llo[c]), std::fabs(lhi[c])));
             }
         }
@@ -224,18 +257,18 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
         for (size_t i = 0; i < n; ++i) scan[i] = int(i);
         auto box_frame = [&](int leaf) { // a moving sphere keeps its world box: the reference tests that box (bvh.rs:31) before
                                          // evaluating the sphere at a time that may lie outside [time0, time1] (main.rs:86)
-            const rt1w_flat_prim &fp = low.prims[bvh.prim_order[leaf]];
+            const rt1w_flat_prim &fp = dev[bvh.prim_order[leaf]];
             return fp.kind == RT1W_NODE_MOVING_SPHERE ? -1 : fp.frame;
         };
         auto is_sphere = [&](int leaf) { // plain spheres get an f32 discriminant screen (kernels.cuh: flat_is_sphere)
-            const rt1w_flat_prim &fp = low.prims[bvh.prim_order[leaf]];
+            const rt1w_flat_prim &fp = dev[bvh.prim_order[leaf]];
             return fp.kind == RT1W_NODE_SPHERE ? 1 : 0;
         };
         std::stable_sort(scan.begin(), scan.end(), [&](int a, int b) {
             return box_frame(a) != box_frame(b) ? box_frame(a) < box_frame(b) : is_sphere(a) < is_sphere(b);
         });
         for (size_t k = 0; k < n; ++k) {
-            const rt1w_flat_prim &fp = low.prims[bvh.prim_order[scan[k]]];
+            const rt1w_flat_prim &fp = dev[bvh.prim_order[scan[k]]];
             const int bf = box_frame(scan[k]);
             double dlo[3], dhi[3];
             if (bf < 0) {
@@ -305,7 +338,7 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     v.flat = flat ? 1 : 0;
     s->material_mask = low.material_mask;
     s->prims = low.prims;
-    s->info.n_prims = int32_t(n), s->info.n_bvh_nodes = int32_t(bvh.nodes.size()), s->info.n_frames = int32_t(low.frames.size());
+    s->info.n_prims = int32_t(low.prims.size()), s->info.n_bvh_nodes = int32_t(bvh.nodes.size()), s->info.n_frames = int32_t(low.frames.size());
     s->info.n_lights = int32_t(low.lights.size()), s->info.bvh_depth = bvh.depth, s->info.material_mask = low.material_mask;
     s->info.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     s->info.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();

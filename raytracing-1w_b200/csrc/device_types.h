@@ -22,7 +22,13 @@ enum PrimType : int {
     P_YZ_RECT = 4,
     P_MEDIUM_SPHERE = 5,
     P_MEDIUM_BOX = 6,
+    P_BOX = 7, // AABox (aabox.rs): its six rectangles as one device primitive; the side travels with the leaf index
 };
+
+// A hit names its primitive as leaf index | side << 28 (side: 0 except for P_BOX, where it is the
+// rectangle's position in aabox.rs:29-76: XY@z1, XY@z0, XZ@y1, XZ@y0, YZ@x1, YZ@x0).
+constexpr int kLeafBits = 28;
+constexpr int kLeafMask = (1 << kLeafBits) - 1;
 
 enum PrimFlags : int { PF_FLIP_FACE = 1 };
 
@@ -44,6 +50,7 @@ static inline uint32_t pack_meta(int type, int flags, int mat_type, int mat_id) 
 //   moving sphere : p0..2 = center0, p3 = radius, f0..2 = center1-center0, f3 = time0, f4 = 1/(time1-time0)
 //   medium sphere : p0..2 = center, p3 = radius, q0 = -1/density
 //   medium box    : p0..2 = box min, p3 = -1/density, q0..2 = box max
+//   box           : p0..2 = box min, q0..2 = box max
 struct DPrim {
     double p[4];
     union {

@@ -193,6 +193,38 @@ RT1W_DEV bool hit_rect(const LocalRay &l, int ax, double a0, double a1, double b
     return true;
 }
 
+// 1 / d with |1/d| capped at 1e18: slab distances of an axis the ray is parallel to stay finite and keep their sign
+RT1W_DEV float rcp_capped(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(copysignf(fmaxf(fabsf(d), 1e-18f), d)));
+    return r;
+}
+
+// AABox (aabox.rs:22-103) = six rectangles, tested for the closest accepted root.  The device keeps the box
+// as one primitive and runs the rectangle test (hit_rect, shared with the plain rectangles so that a warp
+// mixing walls and box sides stays on one code path) on ONE side in the common case: the side an f32 slab
+// computation names as the entry (origin outside: an accepted entry is the closest root of the six) or, when
+// the entry lies before t_min, the exit; then the other of the two.  If both fail - f32 picked the wrong
+// neighbour at an edge, or the ray misses the box - the remaining sides are tested like the reference does,
+// closest root wins.
+// Sides are numbered as aabox.rs:29-76 lists them: XY@z1, XY@z0, XZ@y1, XZ@y0, YZ@x1, YZ@x0.
+// returns the first side to test | the second one << 4
+RT1W_DEV int box_first_sides(const LocalRay &l, double x0, double y0, double z0, double x1, double y1, double z1) {
+    const float ix = rcp_capped(float(l.dx)), iy = rcp_capped(float(l.dy)), iz = rcp_capped(float(l.dz));
+    const float ax = float(x0 - l.ox) * ix, bx = float(x1 - l.ox) * ix;
+    const float ay = float(y0 - l.oy) * iy, by = float(y1 - l.oy) * iy;
+    const float az = float(z0 - l.oz) * iz, bz = float(z1 - l.oz) * iz;
+    const float fx = fminf(ax, bx), fy = fminf(ay, by), fz = fminf(az, bz); // front planes
+    const float kx = fmaxf(ax, bx), ky = fmaxf(ay, by), kz = fmaxf(az, bz); // back planes
+    const int a_in = fx >= fy ? (fx >= fz ? 0 : 2) : (fy >= fz ? 1 : 2);    // entry: the front plane crossed last
+    const int a_out = kx <= ky ? (kx <= kz ? 0 : 2) : (ky <= kz ? 1 : 2);   // exit: the back plane crossed first
+    // entering a positive-going axis happens at the box minimum, leaving it at the maximum
+    const int s_in = (2 - a_in) * 2 + ((a_in == 0 ? ix : (a_in == 1 ? iy : iz)) > 0.0f ? 1 : 0);
+    const int s_out = (2 - a_out) * 2 + ((a_out == 0 ? ix : (a_out == 1 ? iy : iz)) > 0.0f ? 0 : 1);
+    const bool entry_first = fmaxf(fmaxf(fx, fy), fz) >= float(kTMin);
+    return entry_first ? (s_in | (s_out << 4)) : (s_out | (s_in << 4));
+}
+
 template <bool EXACT>
 RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, double ray_length, double tmin, double tmax,
                             const MediumRng &mr, uint32_t id, double &t) {
@@ -213,14 +245,48 @@ RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, d
 // path).  Returns true and the hit parameter when it lands in [t_min, tmax].
 // `frames`: the wrapper frames (global memory, or the flat scan's shared-memory copies).
 // MEDIA = false compiles the ConstantMedium cases out (scenes without media: no Philox, no f64 slabs in the loop).
-template <bool EXACT, bool MEDIA>
-RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t) {
+// `box_sides`: for a P_BOX the caller passes 0 on the first call and calls again while it comes back non-zero
+// (sides still to test); `side` is written with the side tested by this call.
+// BOXES = false compiles the P_BOX case out (the flat scan keeps the six rectangles, api.cu).
+template <bool EXACT, bool MEDIA, bool BOXES>
+RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t,
+                       uint32_t &box_sides, int &side) {
     const double2 *w = reinterpret_cast<const double2 *>(P);
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3); // q2 | meta | frame
     const uint32_t meta = uint32_t(tail.z);
     const int type = int(meta & 15u);
     const double2 p01 = w[0], p23 = w[1];
     const LocalRay l = to_local(tail.w < 0 ? nullptr : frame_xf(frames, tail.w), r);
+    if (type == P_XY_RECT || type == P_XZ_RECT || type == P_YZ_RECT || (BOXES && type == P_BOX)) { // one rectangle test
+        int ax = P_YZ_RECT - type;
+        double a0 = p01.x, a1 = p01.y, b0 = p23.x, b1 = p23.y, k = w[2].x;
+        if (BOXES && type == P_BOX) {
+            const double2 q01 = w[2];
+            const double x0 = p01.x, y0 = p01.y, z0 = p23.x, x1 = q01.x, y1 = q01.y, z1 = __hiloint2double(tail.y, tail.x);
+            const bool first = box_sides == 0u;
+            if (first) { // sides left to test in bits 0..5, the one to test second in bits 8..10
+                const int two = box_first_sides(l, x0, y0, z0, x1, y1, z1);
+                side = two & 15;
+                box_sides = 0x3fu | (uint32_t((two >> 4) | 8) << 8);
+            } else if (box_sides >> 8) {
+                side = int(box_sides >> 8) & 7;
+                box_sides &= 0x3fu;
+            } else {
+                side = __ffs(int(box_sides)) - 1;
+            }
+            box_sides &= ~(1u << side);
+            ax = 2 - (side >> 1);
+            const bool low_plane = (side & 1) != 0;
+            k = ax == 0 ? (low_plane ? x0 : x1) : (ax == 1 ? (low_plane ? y0 : y1) : (low_plane ? z0 : z1));
+            a0 = ax == 0 ? y0 : x0, a1 = ax == 0 ? y1 : x1;
+            b0 = ax == 2 ? y0 : z0, b1 = ax == 2 ? y1 : z1;
+            const bool hit = hit_rect(l, ax, a0, a1, b0, b1, k, kTMin, tmax, t);
+            if (first && hit) box_sides = 0u; // the side f32 named was right: nothing closer on this box
+            if ((box_sides & 0x3fu) == 0u) box_sides = 0u;
+            return hit;
+        }
+        return hit_rect(l, ax, a0, a1, b0, b1, k, kTMin, tmax, t);
+    }
     switch (type) {
     case P_SPHERE: return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
     case P_MOVING_SPHERE: { // moving_sphere.rs:23-26,31-48
@@ -228,9 +294,6 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
         const double s = double((r.time - f.w) * __int_as_float(tail.x));
         return hit_sphere(l, p01.x + s * double(f.x), p01.y + s * double(f.y), p23.x + s * double(f.z), p23.y, kTMin, tmax, t);
     }
-    case P_XY_RECT:
-    case P_XZ_RECT:
-    case P_YZ_RECT: return hit_rect(l, P_YZ_RECT - type, p01.x, p01.y, p23.x, p23.y, w[2].x, kTMin, tmax, t);
     case P_MEDIUM_SPHERE: { // boundary.hit(-inf, inf) then boundary.hit(t1 + 0.0001, inf), constant_medium.rs:58-72
         if (!MEDIA) return false;
         double r0, r1;
@@ -343,11 +406,15 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
         if (!alive) break;
         const uint32_t first = ref & 0x1fffffffu, count = ref >> 29;
         for (uint32_t i = 0; i < count; ++i) {
-            double t;
-            if (hit_prim<EXACT, MEDIA>(sc, sc.frames, sc.prims + (first + i), int(first + i), r, best, mr, t)) {
-                best = t, best_leaf = int(first + i);
-                bestf = __double2float_ru(t);
-            }
+            uint32_t box_sides = 0u;
+            do {
+                double t;
+                int side = 0;
+                if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + (first + i), int(first + i), r, best, mr, t, box_sides, side)) {
+                    best = t, best_leaf = int(first + i) | (side << kLeafBits);
+                    bestf = __double2float_ru(t);
+                }
+            } while (box_sides != 0u);
         }
         alive = pop();
     }
@@ -419,11 +486,6 @@ RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the 
 struct SlabRayF {
     float ix, iy, iz, ox, oy, oz; // 1/d and -o/d
 };
-RT1W_DEV float rcp_capped(float d) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(copysignf(fmaxf(fabsf(d), 1e-18f), d)));
-    return r;
-}
 RT1W_DEV SlabRayF slab_ray(double ox, double oy, double oz, float dx, float dy, float dz) {
     SlabRayF s;
     s.ix = rcp_capped(dx), s.iy = rcp_capped(dy), s.iz = rcp_capped(dz);
@@ -503,7 +565,9 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
         cand &= ~(1u << k);
         const int leaf = __float_as_int(fs.lo[k].w);
         double t;
-        if (hit_prim<EXACT, MEDIA>(sc, fs.frames, fs.prims + leaf, leaf, r, best, mr, t)) {
+        uint32_t box_sides = 0u;
+        int side = 0;
+        if (hit_prim<EXACT, MEDIA, false>(sc, fs.frames, fs.prims + leaf, leaf, r, best, mr, t, box_sides, side)) {
             best = t, best_leaf = leaf;
             bestf = __double2float_ru(t) * 1.000001f;
         }
@@ -543,12 +607,15 @@ RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
 }
 
 // P: the primitive's record, frames: the wrapper frames (global memory or the flat scan's shared-memory copies).
-template <bool WANT_UV> RT1W_DEV_BIG HitInfo finalize_hit(const DPrim *P, const DFrame *frames, const Ray &r, double t) {
+// `side`: which rectangle of a P_BOX was hit (see kLeafBits).
+template <bool WANT_UV> RT1W_DEV_BIG HitInfo finalize_hit(const DPrim *P, const DFrame *frames, int side, const Ray &r, double t) {
     HitInfo h;
     const double2 *w = reinterpret_cast<const double2 *>(P);
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3);
     h.meta = uint32_t(tail.z);
     h.type = int(h.meta & 15u);
+    const bool box = h.type == P_BOX;
+    if (box) h.type = P_XY_RECT + (side >> 1); // the sides come in the order XY, XY, XZ, XZ, YZ, YZ (aabox.rs:29-76)
     const int frame = tail.w;
     // ray.at(t) is invariant under the rigid wrappers; evaluate it once in world space
     h.px = r.ox + t * double(r.dx), h.py = r.oy + t * double(r.dy), h.pz = r.oz + t * double(r.dz);
@@ -590,8 +657,15 @@ template <bool WANT_UV> RT1W_DEV_BIG HitInfo finalize_hit(const DPrim *P, const 
         if (WANT_UV) { // aarect.rs:60-61
             const double2 p01 = w[0], p23 = w[1];
             const double a = h.type == P_YZ_RECT ? ly : lx, b = h.type == P_XY_RECT ? ly : lz;
-            h.u = float((a - p01.x) / (p01.y - p01.x));
-            h.v = float((b - p23.x) / (p23.y - p23.x));
+            double a0 = p01.x, a1 = p01.y, b0 = p23.x, b1 = p23.y;
+            if (box) { // the side's in-plane intervals out of the box corners
+                const double2 q01 = w[2];
+                const double x0 = p01.x, y0 = p01.y, z0 = p23.x, x1 = q01.x, y1 = q01.y, z1 = __hiloint2double(tail.y, tail.x);
+                a0 = h.type == P_YZ_RECT ? y0 : x0, a1 = h.type == P_YZ_RECT ? y1 : x1;
+                b0 = h.type == P_XY_RECT ? y0 : z0, b1 = h.type == P_XY_RECT ? y1 : z1;
+            }
+            h.u = float((a - a0) / (a1 - a0));
+            h.v = float((b - b0) / (b1 - b0));
         }
         ff = dn < 0.0f;
     }

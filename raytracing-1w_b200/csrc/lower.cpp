@@ -426,6 +426,10 @@ DPrim make_device_prim(const rt1w_flat_prim &fp, const std::vector<DMaterial> &m
         for (int i = 0; i < 4; ++i) d.p[i] = p[i];
         d.q[0] = p[4];
         break;
+    case RT1W_NODE_AABOX: // six rectangles merged by the commit (api.cu): p = min xyz, max xyz
+        type = P_BOX;
+        for (int i = 0; i < 3; ++i) d.p[i] = p[i], d.q[i] = p[3 + i];
+        break;
     case RT1W_NODE_CONSTANT_MEDIUM:
         if (fp.boundary == RT1W_NODE_SPHERE) { // p = center, radius, -1/density
             type = P_MEDIUM_SPHERE;

@@ -162,7 +162,7 @@ template <int MAT>
 RT1W_DEV bool scatter(const RenderArgs &a, const DPrim *prims, const DFrame *frames, const DPerlin *perlins, const DLight *lights, Ray &r,
                       const HitRec &hr, RayC &c, f3 &thr) {
     const DMaterial m = a.sc.materials[hr.meta >> 12];
-    const HitInfo h = finalize_hit<false>(prims + hr.leaf, frames, r, hr.t);
+    const HitInfo h = finalize_hit<false>(prims + (hr.leaf & kLeafMask), frames, hr.leaf >> kLeafBits, r, hr.t);
     const uint32_t depth = c.state & 255u;
     Rng rng;
     path_rng_key(a.rp, c.pixel, rng.k0, rng.k1);
@@ -295,11 +295,11 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
                                   : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
             int mat_type = RT1W_MAT_NONE;
             if (hit) {
-                h.meta = FLAT ? s_flat[0].prims[h.leaf].meta : __ldg(&a.sc.prims[h.leaf].meta);
+                h.meta = FLAT ? s_flat[0].prims[h.leaf & kLeafMask].meta : __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
                 mat_type = int((h.meta >> 8) & 15u);
             }
             if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
-                const HitInfo hi = finalize_hit<false>(prims + h.leaf, frames, r, h.t);
+                const HitInfo hi = finalize_hit<false>(prims + (h.leaf & kLeafMask), frames, h.leaf >> kLeafBits, r, h.t);
                 const f3 e = hi.front_face ? texture_value(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
                 splat(a, c.pixel, thr, e);
             } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
         const bool hit = flat ? closest_hit_flat<true, true>(sc, s_flat, r, mr, s_tn + threadIdx.x, kExtendThreads, -1, t, leaf)
                               : closest_hit<true, true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
         HitInfo h;
-        if (hit) h = finalize_hit<true>(sc.prims + leaf, sc.frames, r, t);
-        if (prim_id) prim_id[i] = hit ? sc.prim_id[leaf] : -1;
+        if (hit) h = finalize_hit<true>(sc.prims + (leaf & kLeafMask), sc.frames, leaf >> kLeafBits, r, t);
+        if (prim_id) prim_id[i] = hit ? sc.prim_id[leaf & kLeafMask] + (leaf >> kLeafBits) : -1; // a box: its first rectangle + the side
         if (t_out) t_out[i] = hit ? float(t) : CUDART_INF_F;
         if (normal3) {
             normal3[3 * i] = hit ? h.normal.x : 0.0f, normal3[3 * i + 1] = hit ? h.normal.y : 0.0f, normal3[3 * i + 2] = hit ? h.normal.z : 0.0f;

@@ -373,6 +373,7 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     if (p.max_depth < 0 || p.max_depth > 255) return fail(RT1W_ERR_UNSUPPORTED, "max_depth must be in [0, 255]");
     if (uint64_t(p.width) * uint64_t(p.height) >= (1ull << 31)) return fail(RT1W_ERR_UNSUPPORTED, "image too large");
     const uint64_t all_paths = uint64_t(p.width) * uint64_t(p.height) * uint64_t(p.sample_end - p.sample_begin);
+    if (p.pool_paths > (1 << 30)) return fail(RT1W_ERR_UNSUPPORTED, "pool_paths must not exceed 2^30");
     uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
     if (p.pool_paths <= 0 && all_paths < want_pool) want_pool = uint32_t((all_paths + 1023u) & ~uint64_t(1023u)); // small renders: one wave holds every path
     if (ctx->pool.allocated < want_pool || (ctx->pool.material_mask & scene->material_mask) != scene->material_mask) {

@@ -83,7 +83,7 @@ struct __align__(16) RayB { // second 16-byte word of a ray slot
 struct __align__(16) RayC { // third word: rest of the ray + the path bookkeeping
     float dz, time;
     uint32_t state; // (sample - sample_begin) << 8 | depth
-    uint32_t pixel; // row * width + column, row 0 = top
+    uint32_t pixel; // the reference's pixel seed j * width + i, row j counted from the bottom (main.rs:964)
 };
 struct __align__(16) HitRec {
     double t;

@@ -70,8 +70,11 @@ RT1W_DEV uint32_t warp_sort_reserve(uint32_t *n_mat, int dest) {
 // A path ends: pixel += throughput * radiance.  A NaN product must reach the sum even when the
 // radiance is zero: the reference turns a NaN pixel SUM into black (color.rs:14-21), and
 // `li / pdf` with pdf == 0 is NaN there whatever li is (main.rs:102).
-RT1W_DEV void splat(const RenderArgs &a, uint32_t pixel, f3 thr, f3 radiance) {
+// `seed`: the path's pixel as the reference numbers it (j * width + i, row j counted from the bottom, main.rs:964).
+RT1W_DEV void splat(const RenderArgs &a, uint32_t seed, f3 thr, f3 radiance) {
     const float c[3] = {thr.x * radiance.x, thr.y * radiance.y, thr.z * radiance.z};
+    const uint32_t j = seed / uint32_t(a.rp.width), col = seed - j * uint32_t(a.rp.width);
+    const uint32_t pixel = (uint32_t(a.rp.height) - 1u - j) * uint32_t(a.rp.width) + col; // main.rs:959: rows are emitted top first
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (c[k] != 0.0f) atomicAdd(a.accum + 3 * size_t(pixel) + k, c[k]);
@@ -103,24 +106,20 @@ RT1W_DEV Ray load_ray(const RayQueue &q, uint32_t i, RayC &c) {
 }
 
 // Philox key/counter of a path: key = (reference pixel seed j*w+i (main.rs:964), seed), counter = (sample, bounce, purpose, block)
-RT1W_DEV void path_rng_key(const DRenderParams &rp, uint32_t pixel, uint32_t &k0, uint32_t &k1) {
-    const uint32_t row = pixel / uint32_t(rp.width), col = pixel - row * uint32_t(rp.width);
-    const uint32_t j = uint32_t(rp.height) - 1u - row;
-    k0 = j * uint32_t(rp.width) + col;
-    k1 = rp.seed_lo;
-}
+RT1W_DEV void path_rng_key(const DRenderParams &rp, uint32_t seed, uint32_t &k0, uint32_t &k1) { k0 = seed, k1 = rp.seed_lo; }
 RT1W_DEV uint32_t purpose_word(const DRenderParams &rp, uint32_t stream) { return stream ^ (rp.seed_hi << 4); }
 
 // ------------------------------------------------------------------------------------------
 // a new camera path (main.rs:968-971, camera.rs:61-73, math.rs:30-37)
 // ------------------------------------------------------------------------------------------
-RT1W_DEV Ray generate_ray(const RenderArgs &a, unsigned long long k, uint32_t &state, uint32_t &pixel_out) {
-    const uint32_t sample_rel = uint32_t(k / a.rp.n_pixels);
-    const uint32_t pixel = uint32_t(k - (unsigned long long)sample_rel * a.rp.n_pixels);
-    const uint32_t row = pixel / uint32_t(a.rp.width), col = pixel - row * uint32_t(a.rp.width);
-    const uint32_t j = uint32_t(a.rp.height) - 1u - row; // main.rs:959: rows are emitted top first
+// Path number path0 + i of the render = (sample s0 + (p0 + i) / n_pixels, pixel seed (p0 + i) % n_pixels) with
+// s0 = path0 / n_pixels, p0 = path0 % n_pixels split once per CTA (64-bit) instead of once per path.
+RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t s0, uint32_t p0, uint32_t i, uint32_t &state, uint32_t &seed_out) {
+    const uint32_t q = p0 + i, ds = q / a.rp.n_pixels;
+    const uint32_t seed = q - ds * a.rp.n_pixels, sample_rel = s0 + ds;
+    const uint32_t j = seed / uint32_t(a.rp.width), col = seed - j * uint32_t(a.rp.width);
     Rng rng;
-    rng.k0 = j * uint32_t(a.rp.width) + col, rng.k1 = a.rp.seed_lo;
+    rng.k0 = seed, rng.k1 = a.rp.seed_lo;
     rng.c0 = uint32_t(a.rp.sample_begin) + sample_rel, rng.c1 = 0, rng.c2 = purpose_word(a.rp, RNG_CAMERA), rng.block = 0;
     const Philox4 x = rng.next4();
     const double s = (double(col) + double(u01(x.x))) / double(a.rp.width - 1);  // main.rs:968
@@ -148,7 +147,7 @@ RT1W_DEV Ray generate_ray(const RenderArgs &a, unsigned long long k, uint32_t &s
     r.ox = a.cam.origin[0] + offx, r.oy = a.cam.origin[1] + offy, r.oz = a.cam.origin[2] + offz;
     r.time = a.cam.time0 + (a.cam.time1 - a.cam.time0) * u01(x.z); // camera.rs:71
     state = sample_rel << 8;
-    pixel_out = pixel;
+    seed_out = seed;
     return r;
 }
 
@@ -213,6 +212,11 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
     __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kWaveThreads];
     __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
     __shared__ unsigned int s_traced;
+    // the wave's layout, read back from shared memory inside the loop instead of pinning a dozen registers
+    struct Layout {
+        uint32_t off1, off2, off3, off4, cnt0, cnt1, cnt2, cnt3, total, gen_s0, gen_p0;
+    };
+    __shared__ Layout s_layout;
     uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
     FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
     float *s_tn = reinterpret_cast<float *>(s_raw + sizeof(FlatScene)); // entry distances, [primitive][thread]
@@ -237,7 +241,14 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
     }
     if (blockIdx.x * blockDim.x >= total) return;
 
-    if (threadIdx.x == 0) s_traced = 0;
+    if (threadIdx.x == 0) {
+        s_traced = 0;
+        Layout l;
+        l.off1 = off1, l.off2 = off2, l.off3 = off3, l.off4 = off4, l.cnt0 = cnt0, l.cnt1 = cnt1, l.cnt2 = cnt2, l.cnt3 = cnt3, l.total = total;
+        // path number path0 + i = (sample gen_s0 + (gen_p0 + i) / n_pixels, pixel (gen_p0 + i) % n_pixels): one 64-bit division per CTA
+        l.gen_s0 = uint32_t(path0 / a.rp.n_pixels), l.gen_p0 = uint32_t(path0 - (unsigned long long)l.gen_s0 * a.rp.n_pixels);
+        s_layout = l;
+    }
     if (FLAT) flat_stage(a.sc, s_flat[0]);
     const DPerlin *perlins = a.sc.perlins;
     if (perlin_in_smem) {
@@ -252,19 +263,22 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
 
     const DPrim *prims = FLAT ? s_flat[0].prims : a.sc.prims;
     const DFrame *frames = FLAT ? s_flat[0].frames : a.sc.frames;
+    const volatile Layout &lay = s_layout;
     const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
     uint32_t traced = 0;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < lay.total; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         Ray r;
         RayC c;
         f3 thr;
         bool alive = false;
         int skip_leaf = -1; // the primitive the ray starts on
+        const uint32_t off4 = lay.off4;
         if (i < off4) { // a hit queued by the previous wave: scatter
+            const uint32_t off1 = lay.off1, off2 = lay.off2, off3 = lay.off3;
             const int seg = i < off1 ? 0 : (i < off2 ? 1 : (i < off3 ? 2 : 3)); // warp-uniform
             const uint32_t j = i - (seg == 0 ? 0u : (seg == 1 ? off1 : (seg == 2 ? off2 : off3)));
-            if (j < (seg == 0 ? cnt0 : (seg == 1 ? cnt1 : (seg == 2 ? cnt2 : cnt3)))) {
+            if (j < (seg == 0 ? lay.cnt0 : (seg == 1 ? lay.cnt1 : (seg == 2 ? lay.cnt2 : lay.cnt3)))) {
                 const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
                 r = load_ray(in, j, c);
                 const HitRec hr = in.h[j];
@@ -276,8 +290,8 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
                 else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
                 else alive = scatter<RT1W_MAT_ISOTROPIC>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
             }
-        } else if (i < total) { // a new camera path
-            r = generate_ray(a, path0 + (i - off4), c.state, c.pixel);
+        } else if (i < lay.total) { // a new camera path
+            r = generate_ray(a, lay.gen_s0, lay.gen_p0, i - off4, c.state, c.pixel);
             thr = mk3(1.0f, 1.0f, 1.0f);
             alive = true;
         }

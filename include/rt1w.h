@@ -160,11 +160,13 @@ typedef struct rt1w_camera {
 
 #define RT1W_FLAG_STATS 1u   /* also accumulate per-pixel clamped sum and sum of squares (test statistic) */
 #define RT1W_FLAG_PROFILE 2u /* bracket every kernel launch with CUDA events and fill rt1w_render_stats.kernel_ms (slower) */
+/* BVH scenes: which wave kernel traverses (default: by BVH size).  Both return the same closest hits; parity tests force each. */
+#define RT1W_FLAG_BVH_LOCKSTEP 4u   /* a warp runs its 32 rays to the end together (short, even traversals) */
+#define RT1W_FLAG_BVH_PERSISTENT 8u /* lanes take a new ray as soon as theirs is done (long, uneven traversals) */
 
 /* kernel slots of rt1w_render_stats.kernel_ms / kernel_launches */
-#define RT1W_KERNEL_WAVE 0   /* k_wave: scatter queued hits / start camera paths, closest hit, regroup per material */
-#define RT1W_KERNEL_FINISH 1 /* k_finish: the last sparse waves, every remaining path run to its end by one thread */
-#define RT1W_KERNEL_COUNT 7  /* slots 2..6 reserved */
+#define RT1W_KERNEL_WAVE 0  /* k_wave / k_wave_bvh: scatter queued hits / start camera paths, closest hit, regroup per material */
+#define RT1W_KERNEL_COUNT 7 /* slots 1..6 reserved */
 
 typedef struct rt1w_render_params {
     int32_t width;          /* image_width  (main.rs:799) */

@@ -18,6 +18,8 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC, MAT
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE, TEX_PERLIN = range(5)
 FLAG_STATS = 1
 FLAG_PROFILE = 2
+FLAG_BVH_LOCKSTEP = 4
+FLAG_BVH_PERSISTENT = 8
 
 SCENE_IDS = {"random_scene": 0, "two_spheres": 1, "two_perlin_spheres": 2, "earth": 3, "simple_light": 4,
              "cornel_box": 5, "cornel_smoke": 6, "final_scene": 7, "stress": 8, "one_weekend": 9}
@@ -71,7 +73,7 @@ class RenderParams(C.Structure):
                 ("stat_clamp", C.c_double), ("pool_paths", C.c_int32), ("reserved", C.c_int32)]
 
 
-KERNEL_NAMES = ["wave", "finish", "-", "-", "-", "-", "-"]  # slot = 2 + rt1w_material_type for the shade kernels
+KERNEL_NAMES = ["wave", "-", "-", "-", "-", "-", "-"]  # slot = 2 + rt1w_material_type for the shade kernels
 
 
 class RenderStats(C.Structure):

@@ -346,80 +346,97 @@ RT1W_DEV bool slab(const float4 lo, const float4 hi, const SlabRay &s, float tma
 // Node references on the traversal stack: primitive count in the top 3 bits, left_first below.
 RT1W_DEV uint32_t node_ref(float4 n0, float4 n1) { return (__float_as_uint(n1.w) << 29) | __float_as_uint(n0.w); }
 
-// `stack` points at this thread's column of the shared short stack (stride = blockDim.x); an entry is
-// (node reference, entry distance) so that subtrees the current best hit already beats are dropped on pop.
-// while-while traversal: every lane descends to its next leaf before any lane runs the (f64) primitive
-// tests, so those run with most of the warp converged.
+// Traversal state of one ray, resumable step by step (the wave kernel interleaves the steps of a warp's rays
+// with refills of its idle lanes; the parity kernel just runs them to the end).
+// The stack holds (node reference, entry distance) so that subtrees the best hit already beats are dropped
+// on pop; its first kStackSmem entries live in the thread's column of a shared-memory array (stride =
+// blockDim.x), deeper ones in a local-memory overflow.
+constexpr uint32_t kTravDone = 0xffffffffu;
+struct Trav {
+    SlabRay s;
+    double best;    // closest accepted root so far
+    float bestf;    // its f32 upper bound, for the node tests
+    int best_leaf;  // leaf | side << kLeafBits, or -1
+    uint32_t ref;   // node to visit next: interior (count bits 0), leaf, or kTravDone
+    int sp;
+};
+
+RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, Trav &T) {
+    T.s.ox = float(r.ox), T.s.oy = float(r.oy), T.s.oz = float(r.oz);
+    T.s.ix = 1.0f / r.dx, T.s.iy = 1.0f / r.dy, T.s.iz = 1.0f / r.dz;
+    T.best = CUDART_INF, T.bestf = CUDART_INF_F, T.best_leaf = -1, T.sp = 0;
+    const float4 n0 = __ldg(sc.nodes), n1 = __ldg(sc.nodes + 1);
+    float tn;
+    T.ref = slab(n0, n1, T.s, T.bestf, tn) ? node_ref(n0, n1) : kTravDone;
+}
+
+RT1W_DEV bool trav_interior(const Trav &T) { return (T.ref >> 29) == 0u; }
+RT1W_DEV bool trav_done(const Trav &T) { return T.ref == kTravDone; }
+
+RT1W_DEV void trav_pop(Trav &T, const uint2 *stack, int stride, const uint2 *overflow) { // next stacked subtree that can still hold a closer hit
+    while (T.sp > 0) {
+        --T.sp;
+        const uint2 e = T.sp < kStackSmem ? stack[T.sp * stride] : overflow[T.sp - kStackSmem];
+        if (__uint_as_float(e.y) <= T.bestf) {
+            T.ref = e.x;
+            return;
+        }
+    }
+    T.ref = kTravDone;
+}
+
+// one interior node: both children (one 64-byte pair) tested, nearer one first
+RT1W_DEV void trav_step_interior(const SceneView &sc, Trav &T, uint2 *stack, int stride, uint2 *overflow) {
+    const float4 *c = sc.nodes + 2 * T.ref;
+    const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
+    float tl, tr;
+    const bool hl = slab(l0, l1, T.s, T.bestf, tl), hr = slab(r0, r1, T.s, T.bestf, tr);
+    const uint32_t refl = node_ref(l0, l1), refr = node_ref(r0, r1);
+    if (hl && hr) {
+        const bool left_near = tl <= tr;
+        const uint2 far_e = make_uint2(left_near ? refr : refl, __float_as_uint(left_near ? tr : tl));
+        if (T.sp < kStackSmem) stack[T.sp * stride] = far_e;
+        else overflow[T.sp - kStackSmem] = far_e;
+        ++T.sp;
+        T.ref = left_near ? refl : refr;
+    } else if (hl || hr) {
+        T.ref = hl ? refl : refr;
+    } else {
+        trav_pop(T, stack, stride, overflow);
+    }
+}
+
+// one leaf: its primitives solved in f64, then the next subtree
+template <bool EXACT, bool MEDIA>
+RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng &mr, Trav &T, const uint2 *stack, int stride, const uint2 *overflow) {
+    const uint32_t first = T.ref & 0x1fffffffu, count = T.ref >> 29;
+    for (uint32_t i = 0; i < count; ++i) {
+        uint32_t box_sides = 0u;
+        do {
+            double t;
+            int side = 0;
+            if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + (first + i), int(first + i), r, T.best, mr, t, box_sides, side)) {
+                T.best = t, T.best_leaf = int(first + i) | (side << kLeafBits);
+                T.bestf = __double2float_ru(t);
+            }
+        } while (box_sides != 0u);
+    }
+    trav_pop(T, stack, stride, overflow);
+}
+
+// while-while traversal to the end: every lane descends to its next leaf before any lane runs the (f64)
+// primitive tests, so those run with most of the warp converged.
 template <bool EXACT, bool MEDIA>
 RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
-    SlabRay s;
-    s.ox = float(r.ox), s.oy = float(r.oy), s.oz = float(r.oz);
-    s.ix = 1.0f / r.dx, s.iy = 1.0f / r.dy, s.iz = 1.0f / r.dz;
-    double best = CUDART_INF;
-    float bestf = CUDART_INF_F;
-    int best_leaf = -1;
     uint2 overflow[kStackLocal];
-    int sp = 0;
-    uint32_t ref;
-    {
-        const float4 n0 = __ldg(sc.nodes), n1 = __ldg(sc.nodes + 1);
-        float tn;
-        if (!slab(n0, n1, s, bestf, tn)) {
-            t_best = best, leaf_best = -1;
-            return false;
-        }
-        ref = node_ref(n0, n1);
+    Trav T;
+    trav_begin(sc, r, T);
+    while (!trav_done(T)) {
+        while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, overflow);
+        if (!trav_done(T)) trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, overflow);
     }
-    auto pop = [&]() -> bool { // next stacked subtree that can still contain a closer hit
-        while (sp > 0) {
-            --sp;
-            const uint2 e = sp < kStackSmem ? stack[sp * stride] : overflow[sp - kStackSmem];
-            if (__uint_as_float(e.y) <= bestf) {
-                ref = e.x;
-                return true;
-            }
-        }
-        return false;
-    };
-    bool alive = true;
-    while (alive) {
-        while ((ref >> 29) == 0u) { // interior: children at ref, ref + 1 (one 64-byte pair)
-            const float4 *c = sc.nodes + 2 * ref;
-            const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
-            float tl, tr;
-            const bool hl = slab(l0, l1, s, bestf, tl), hr = slab(r0, r1, s, bestf, tr);
-            const uint32_t refl = node_ref(l0, l1), refr = node_ref(r0, r1);
-            if (hl && hr) {
-                const bool left_near = tl <= tr;
-                const uint2 far_e = make_uint2(left_near ? refr : refl, __float_as_uint(left_near ? tr : tl));
-                if (sp < kStackSmem) stack[sp * stride] = far_e;
-                else overflow[sp - kStackSmem] = far_e;
-                ++sp;
-                ref = left_near ? refl : refr;
-            } else if (hl || hr) {
-                ref = hl ? refl : refr;
-            } else if (!pop()) {
-                alive = false;
-                break;
-            }
-        }
-        if (!alive) break;
-        const uint32_t first = ref & 0x1fffffffu, count = ref >> 29;
-        for (uint32_t i = 0; i < count; ++i) {
-            uint32_t box_sides = 0u;
-            do {
-                double t;
-                int side = 0;
-                if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + (first + i), int(first + i), r, best, mr, t, box_sides, side)) {
-                    best = t, best_leaf = int(first + i) | (side << kLeafBits);
-                    bestf = __double2float_ru(t);
-                }
-            } while (box_sides != 0u);
-        }
-        alive = pop();
-    }
-    t_best = best, leaf_best = best_leaf;
-    return best_leaf >= 0;
+    t_best = T.best, leaf_best = T.best_leaf;
+    return T.best_leaf >= 0;
 }
 
 // Small scenes (<= kFlatMax primitives and <= kFlatMaxFrames wrapper chains, e.g. the 13 + 1 of the Cornell

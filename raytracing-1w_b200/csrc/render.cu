@@ -345,6 +345,235 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
 }
 
 // ------------------------------------------------------------------------------------------
+// the wave kernel of BVH scenes: persistent warps, rays replaced lane by lane
+// ------------------------------------------------------------------------------------------
+// BVH traversal lengths vary wildly from ray to ray (a 1 M-sphere scene: 5 of 32 lanes busy when a warp
+// runs 32 rays to the end together), while scattering wants a whole warp on one material.  So a warp
+// alternates between two jobs:
+//   produce   takes the next 32-item block of its CTA's share of the wave (one material, or new camera
+//             paths), scatters / generates with all 32 lanes, and parks the surviving rays + path state in
+//             the warp's private ring buffer in shared memory;
+//   traverse  bounded while-while rounds (interior steps until the next leaf, then the f64 primitive
+//             tests); a lane whose ray is done hands the path over (queue of the material it landed on,
+//             or the pixel) and takes the next ray out of the ring at once.
+// The traversals in flight simply wait in registers while the warp produces.
+#ifndef RT1W_INNER_STEPS
+#define RT1W_INNER_STEPS 32 // at most this many interior steps per round
+#endif
+#ifndef RT1W_LEAF_LANES
+#define RT1W_LEAF_LANES 24 // a round's interior steps stop once this many lanes wait at a leaf
+#endif
+constexpr int kPersistentFromNodes = 32768;
+constexpr int kRing = 64; // rays per warp ring; a block is produced whenever 32 entries are free
+
+struct WaveLayout { // thread index space of a wave: [lambertian hits | metal | dielectric | isotropic | new paths]
+    uint32_t off1, off2, off3, off4, cnt0, cnt1, cnt2, cnt3, total, gen_s0, gen_p0;
+};
+
+struct __align__(16) RingRay { // 64 bytes: a ray and the state of its path, between scatter and traversal
+    double ox, oy, oz;
+    float dx, dy, dz, time;
+    float tr, tg, tb;
+    uint32_t state, pixel;
+    uint32_t pad;
+};
+static_assert(sizeof(RingRay) == 64, "RingRay must be 4 x 16 bytes");
+
+template <bool MEDIA>
+__global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
+    k_wave_bvh(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
+    extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
+    __shared__ uint2 s_stack[kStackSmem * kWaveThreads];
+    __shared__ RingRay s_ring[(kWaveThreads / 32) * kRing];
+    __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
+    __shared__ unsigned int s_traced, s_next;
+    __shared__ WaveLayout s_layout;
+
+    Counters *ctr = a.pool.ctr;
+    const int nxt = slot == 2 ? 0 : slot + 1, clr = nxt == 2 ? 0 : nxt + 1;
+    uint32_t total;
+    {
+        const uint32_t cnt0 = ctr->n_mat[slot][scatter_mat(0)], cnt1 = ctr->n_mat[slot][scatter_mat(1)];
+        const uint32_t cnt2 = ctr->n_mat[slot][scatter_mat(2)], cnt3 = ctr->n_mat[slot][scatter_mat(3)];
+        const uint32_t off1 = (cnt0 + 31u) & ~31u, off2 = off1 + ((cnt1 + 31u) & ~31u), off3 = off2 + ((cnt2 + 31u) & ~31u);
+        const uint32_t off4 = off3 + ((cnt3 + 31u) & ~31u);
+        const uint32_t queued = cnt0 + cnt1 + cnt2 + cnt3;
+        const unsigned long long path0 = ctr->next_path[slot];
+        const unsigned long long left = a.rp.total_paths - min(a.rp.total_paths, path0);
+        const uint32_t n_new = uint32_t(min((unsigned long long)(a.pool.capacity - min(a.pool.capacity, queued)), left));
+        total = off4 + n_new;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { // hand the counters over: nobody else writes these slots during this wave
+            ctr->next_path[nxt] = path0 + n_new;
+#pragma unroll
+            for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[clr][q] = 0;
+        }
+        if (threadIdx.x == 0) {
+            s_traced = 0, s_next = 0;
+            WaveLayout l;
+            l.off1 = off1, l.off2 = off2, l.off3 = off3, l.off4 = off4, l.cnt0 = cnt0, l.cnt1 = cnt1, l.cnt2 = cnt2, l.cnt3 = cnt3, l.total = total;
+            l.gen_s0 = uint32_t(path0 / a.rp.n_pixels), l.gen_p0 = uint32_t(path0 - (unsigned long long)l.gen_s0 * a.rp.n_pixels);
+            s_layout = l;
+        }
+    }
+    // this CTA's share of the wave: the 32-item blocks blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint32_t n_blocks = (total + 31u) >> 5;
+    const uint32_t my_blocks = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+    if (my_blocks == 0u) return;
+
+    const DPerlin *perlins = a.sc.perlins;
+    if (perlin_in_smem) {
+        const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+        perlins = reinterpret_cast<const DPerlin *>(s_dyn);
+    }
+    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
+    __syncthreads();
+
+    const volatile WaveLayout &lay = s_layout;
+    const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
+    const int lane = threadIdx.x & 31;
+    uint2 *stack = s_stack + threadIdx.x;
+    RingRay *ring = s_ring + (threadIdx.x >> 5) * kRing;
+    uint2 overflow[kStackLocal];
+    uint32_t traced = 0;
+    uint32_t ring_rd = 0, ring_cnt = 0; // warp-uniform
+    bool more = true;                   // warp-uniform: the CTA's share still has blocks
+    bool has_ray = false;
+    Ray r;
+    RayC c;
+    f3 thr;
+    Trav T;
+    T.ref = kTravDone;
+    for (;;) {
+        // ---- produce: one 32-item block -> scatter / generate with the whole warp -> surviving rays into the ring
+        if (more && ring_cnt <= uint32_t(kRing - 32)) {
+            uint32_t qb = 0;
+            if (lane == 0) qb = atomicAdd(&s_next, 1u);
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            more = qb + 1u < my_blocks;
+            if (qb < my_blocks) {
+                const uint32_t i = ((qb * gridDim.x + blockIdx.x) << 5) + uint32_t(lane);
+                Ray nr;
+                RayC nc;
+                f3 nthr;
+                bool alive = false;
+                const uint32_t off4 = lay.off4;
+                if (i < off4) { // a hit queued by the previous wave: scatter (one material per block)
+                    const uint32_t off1 = lay.off1, off2 = lay.off2, off3 = lay.off3;
+                    const int seg = i < off1 ? 0 : (i < off2 ? 1 : (i < off3 ? 2 : 3));
+                    const uint32_t j = i - (seg == 0 ? 0u : (seg == 1 ? off1 : (seg == 2 ? off2 : off3)));
+                    if (j < (seg == 0 ? lay.cnt0 : (seg == 1 ? lay.cnt1 : (seg == 2 ? lay.cnt2 : lay.cnt3)))) {
+                        const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
+                        nr = load_ray(in, j, nc);
+                        const HitRec hr = in.h[j];
+                        const float4 th4 = in.t[j];
+                        nthr = mk3(th4.x, th4.y, th4.z);
+                        if (seg == 0) alive = scatter<RT1W_MAT_LAMBERTIAN>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                        else if (seg == 1) alive = scatter<RT1W_MAT_METAL>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                        else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                        else alive = scatter<RT1W_MAT_ISOTROPIC>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                    }
+                } else if (i < lay.total) { // a new camera path
+                    nr = generate_ray(a, lay.gen_s0, lay.gen_p0, i - off4, nc.state, nc.pixel);
+                    nthr = mk3(1.0f, 1.0f, 1.0f);
+                    alive = true;
+                }
+                const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+                if (alive) {
+                    RingRay e;
+                    e.ox = nr.ox, e.oy = nr.oy, e.oz = nr.oz, e.dx = nr.dx, e.dy = nr.dy, e.dz = nr.dz, e.time = nr.time;
+                    e.tr = nthr.x, e.tg = nthr.y, e.tb = nthr.z, e.state = nc.state, e.pixel = nc.pixel, e.pad = 0;
+                    ring[(ring_rd + ring_cnt + __popc(alive_mask & ((1u << lane) - 1u))) & (kRing - 1)] = e;
+                }
+                ring_cnt += __popc(alive_mask);
+                __syncwarp();
+            }
+        }
+        // ---- idle lanes take rays out of the ring
+        const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+        if (idle != 0u && ring_cnt != 0u) {
+            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            if (!has_ray && rank < ring_cnt) {
+                const RingRay e = ring[(ring_rd + rank) & (kRing - 1)];
+                r.ox = e.ox, r.oy = e.oy, r.oz = e.oz, r.dx = e.dx, r.dy = e.dy, r.dz = e.dz, r.time = e.time;
+                thr = mk3(e.tr, e.tg, e.tb);
+                c.state = e.state, c.pixel = e.pixel;
+                ++traced;
+                trav_begin(a.sc, r, T);
+                has_ray = true;
+            }
+            const uint32_t taken = min(uint32_t(__popc(idle)), ring_cnt);
+            ring_rd = (ring_rd + taken) & (kRing - 1), ring_cnt -= taken;
+            __syncwarp();
+        } else if (idle == 0xffffffffu && !more) {
+            break; // nothing in flight, nothing parked, nothing left to produce
+        }
+        // ---- one while-while round: interior steps until enough lanes wait at a leaf (or finished), then the leaves
+        for (int step = 0; step < RT1W_INNER_STEPS; ++step) {
+            const bool interior = has_ray && trav_interior(T);
+            const unsigned walking = __ballot_sync(0xffffffffu, interior);
+            const unsigned at_leaf = __ballot_sync(0xffffffffu, has_ray && !interior && !trav_done(T));
+            if (walking == 0u || __popc(at_leaf) >= RT1W_LEAF_LANES) break; // every round steps or solves: it always makes progress
+            if (interior) trav_step_interior(a.sc, T, stack, kWaveThreads, overflow);
+        }
+        if (has_ray && !trav_interior(T) && !trav_done(T)) {
+            MediumRng mr = {0, 0, 0, 0, 0};
+            if (MEDIA) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
+                path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
+                mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
+            }
+            trav_step_leaf<false, MEDIA>(a.sc, r, mr, T, stack, kWaveThreads, overflow);
+        }
+        // ---- rays that reached the end: finish the path or hand it to the material it landed on
+        const bool fin = has_ray && trav_done(T);
+        if (__any_sync(0xffffffffu, fin)) {
+            int dest = -1;
+            HitRec h;
+            if (fin) {
+                has_ray = false;
+                const bool hit = T.best_leaf >= 0;
+                h.t = T.best, h.leaf = T.best_leaf;
+                int mat_type = RT1W_MAT_NONE;
+                if (hit) {
+                    h.meta = __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
+                    mat_type = int((h.meta >> 8) & 15u);
+                }
+                if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
+                    const HitInfo hi = finalize_hit<false>(a.sc.prims + (h.leaf & kLeafMask), a.sc.frames, h.leaf >> kLeafBits, r, h.t);
+                    const f3 e = hi.front_face ? texture_value(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
+                    splat(a, c.pixel, thr, e);
+                } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
+                    const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
+                    if (has_background || !finite3(thr)) splat(a, c.pixel, thr, rad);
+                } else {
+                    dest = mat_type;
+                }
+            }
+            __syncwarp();
+            const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
+            if (dest >= 0) {
+                const RayQueue &out = a.pool.mat[parity ^ 1][dest];
+                out.a[e] = make_double2(r.ox, r.oy);
+                RayB b;
+                b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
+                out.b[e] = b;
+                c.dz = r.dz, c.time = r.time;
+                out.c[e] = c;
+                out.t[e] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                out.h[e] = h;
+            }
+        }
+    }
+    // closest-hit queries of this wave -> the render's ray count
+    traced = __reduce_add_sync(0xffffffffu, traced);
+    if (lane == 0 && traced) atomicAdd(&s_traced, traced);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_traced) atomicAdd(&ctr->rays, (unsigned long long)s_traced);
+}
+
+// ------------------------------------------------------------------------------------------
 // closest-hit parity kernel
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant__ SceneView sc, const rt1w_ray *__restrict__ rays, const size_t n,
@@ -436,7 +665,14 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     const int poll_every = 8;
     // grid: every CTA resident at once (SM count x occupancy); the kernel grid-strides over a device-side count
     using WaveKernel = void (*)(const RenderArgs, const int, const int, const int);
-    const WaveKernel kernel = flat ? (media ? k_wave<true, true> : k_wave<true, false>) : (media ? k_wave<false, true> : k_wave<false, false>);
+    // BVH scenes: traversals of a big tree vary too much in length to run a warp's rays in lockstep (1 M spheres:
+    // 5 of 32 lanes busy); small trees are walked faster by the leaner lockstep kernel (measured crossover)
+    bool persistent = args.sc.n_nodes > kPersistentFromNodes;
+    if (args.rp.flags & RT1W_FLAG_BVH_LOCKSTEP) persistent = false;
+    if (args.rp.flags & RT1W_FLAG_BVH_PERSISTENT) persistent = true;
+    const WaveKernel kernel = flat         ? (media ? k_wave<true, true> : k_wave<true, false>)
+                              : persistent ? (media ? k_wave_bvh<true> : k_wave_bvh<false>)
+                                           : (media ? k_wave<false, true> : k_wave<false, false>);
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWaveThreads, perlin_bytes)) != cudaSuccess) return e;

@@ -51,7 +51,7 @@ struct RenderArgs {
     float *stat;  // width*height*6 clamped sum / sum of squares, or nullptr
 };
 
-enum KernelSlot : int { K_WAVE = 0, K_FINISH = 1, K_COUNT = RT1W_KERNEL_COUNT };
+enum KernelSlot : int { K_WAVE = 0, K_COUNT = RT1W_KERNEL_COUNT };
 
 struct WaveStats {
     uint64_t waves = 0, launches = 0, rays = 0;

@@ -96,3 +96,20 @@ def test_depth_limits(rt, gpu_ctx):
     assert st1.rays == 32 * 32 * 4  # exactly one closest-hit query per path
     assert img1.max() == pytest.approx(4 * 15.0)  # only directly visible light (emit 15, main.rs:414-418)
     gsc.close()
+
+
+@pytest.mark.parametrize("name", ["random_scene", "final_scene"])
+def test_bvh_wave_kernels_agree(rt, gpu_ctx, name):
+    """The two wave kernels of BVH scenes (lockstep warps / lanes that take a new ray as soon as theirs is done) find the
+    same closest hits and draw the same Philox numbers: same ray count, same image up to fp32 summation order."""
+    api = rt.api
+    hs = api.HostScene(name, seed=1)
+    gsc = api.Scene(gpu_ctx, hs.desc)
+    cam = hs.camera()
+    a, _, sa = gsc.render(cam, hs.params(width=96, spp=16, seed=5, flags=api.FLAG_BVH_LOCKSTEP))
+    b, _, sb = gsc.render(cam, hs.params(width=96, spp=16, seed=5, flags=api.FLAG_BVH_PERSISTENT))
+    assert sa.rays == sb.rays and sa.paths == sb.paths
+    ok = np.isfinite(a) & np.isfinite(b)
+    assert (np.isfinite(a) == np.isfinite(b)).all()
+    assert np.allclose(a[ok], b[ok], rtol=1e-4, atol=1e-4)
+    gsc.close()

@@ -31,8 +31,11 @@ namespace rt1w {
 
 constexpr double kTMin = 0.001;      // main.rs:62
 constexpr float kPiF = 3.14159265358979323846f;
-constexpr int kStackSmem = 24;       // per-thread short stack entries kept in shared memory
-constexpr int kStackLocal = 40;      // overflow entries (local memory; the builder caps the depth at 62)
+#ifndef RT1W_STACK_SMEM
+#define RT1W_STACK_SMEM 24
+#endif
+constexpr int kStackSmem = RT1W_STACK_SMEM;       // per-thread short stack entries kept in shared memory
+constexpr int kStackLocal = 64 - RT1W_STACK_SMEM; // overflow entries (local memory; the builder caps the depth at 62)
 
 struct SceneView {
     const float4 *nodes;       // 2 x float4 per node
@@ -374,6 +377,7 @@ RT1W_DEV bool trav_interior(const Trav &T) { return (T.ref >> 29) == 0u; }
 RT1W_DEV bool trav_done(const Trav &T) { return T.ref == kTravDone; }
 
 RT1W_DEV void trav_pop(Trav &T, const uint2 *stack, int stride, const uint2 *overflow) { // next stacked subtree that can still hold a closer hit
+    // (taking one entry per step instead of looping here was measured slower: 479 vs 507 Mrays/s on the 1 M-sphere scene)
     while (T.sp > 0) {
         --T.sp;
         const uint2 e = T.sp < kStackSmem ? stack[T.sp * stride] : overflow[T.sp - kStackSmem];

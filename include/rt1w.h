@@ -270,6 +270,13 @@ rt1w_status rt1w_render(rt1w_scene *scene, const rt1w_camera *camera, const rt1w
 rt1w_status rt1w_render_device(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params,
                                float *d_rgb_sum, void *cuda_stream, rt1w_render_stats *stats);
 
+/* Render + the output path of main.rs:992,1003-1007 on the device: the per-pixel sums are resolved to 8-bit
+ * channels (`Color::into_sampled`, `Display for SampledColor`, color.rs:14-21,56-65) before they leave the GPU.
+ * out_rgb8: HOST buffer, width*height*3 bytes, row 0 = top - what the reference prints as its P3 body.
+ * The mean divides by sample_end - sample_begin. */
+rt1w_status rt1w_render_rgb8(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params,
+                             uint8_t *out_rgb8, rt1w_render_stats *stats);
+
 /* Parity hook: closest hit (`world.hit(ray, 0.001, inf)`, main.rs:62) for n
  * host rays.  prim_id = -1 on a miss.  Media draw their free-flight number from
  * Philox keyed by (seed, ray index, primitive id) so a CPU checker can replay it.

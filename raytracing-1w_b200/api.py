@@ -111,7 +111,7 @@ class HostSettings(C.Structure):
 ABI_SYMBOLS = [
     "rt1w_abi_version", "rt1w_last_error", "rt1w_context_create", "rt1w_context_destroy", "rt1w_scene_create",
     "rt1w_scene_destroy", "rt1w_scene_get_info", "rt1w_scene_get_prims", "rt1w_lower_prims", "rt1w_render",
-    "rt1w_render_device", "rt1w_trace_closest", "rt1w_resolve_rgb8", "rt1w_philox4x32",
+    "rt1w_render_device", "rt1w_render_rgb8", "rt1w_trace_closest", "rt1w_resolve_rgb8", "rt1w_philox4x32",
 ]
 
 
@@ -148,6 +148,7 @@ def load_library():
     lib.rt1w_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     lib.rt1w_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     lib.rt1w_trace_closest.argtypes = [vp, vp, C.c_size_t, C.c_uint64, vp, vp, vp, vp, vp]
+    lib.rt1w_render_rgb8.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
     lib.rt1w_resolve_rgb8.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
     lib.rt1w_resolve_rgb8.restype = None
     lib.rt1w_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -473,6 +474,13 @@ class Scene:
         _check(load_library().rt1w_render(self._h, C.byref(camera), C.byref(params), C.c_void_p(out.ctypes.data),
                                           C.c_void_p(stat.ctypes.data) if stat is not None else None, C.byref(st)))
         return st
+
+    def render_rgb8(self, camera, params):
+        """rt1w_render_rgb8: render + resolve on the device; returns (rgb8[h,w,3] uint8, RenderStats)."""
+        out = np.empty((params.height, params.width, 3), dtype=np.uint8)
+        st = RenderStats()
+        _check(load_library().rt1w_render_rgb8(self._h, C.byref(camera), C.byref(params), out.ctypes.data_as(C.c_void_p), C.byref(st)))
+        return out, st
 
     def render_device(self, camera, params, d_ptr, stream=0):
         st = RenderStats()

@@ -87,7 +87,8 @@ struct rt1w_context {
     Pool pool;
     Counters *h_ctr = nullptr; // pinned
     float *d_accum = nullptr, *d_stat = nullptr;
-    size_t accum_pixels = 0, stat_pixels = 0;
+    uint8_t *d_rgb8 = nullptr;
+    size_t accum_pixels = 0, stat_pixels = 0, rgb8_pixels = 0;
     std::mutex lock; // calls on one context are serialised (rt1w.h "Threading")
 };
 
@@ -159,7 +160,7 @@ void rt1w_context_destroy(rt1w_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pool_free(ctx->pool);
-    cudaFree(ctx->d_accum), cudaFree(ctx->d_stat);
+    cudaFree(ctx->d_accum), cudaFree(ctx->d_stat), cudaFree(ctx->d_rgb8);
     cudaFreeHost(ctx->h_ctr);
     cudaEventDestroy(ctx->ev0), cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -453,6 +454,33 @@ rt1w_status rt1w_render(rt1w_scene *scene, const rt1w_camera *camera, const rt1w
     if (st != RT1W_OK) return st;
     RT1W_CUDA(cudaMemcpyAsync(out_rgb_sum, ctx->d_accum, sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
     if (want_stat) RT1W_CUDA(cudaMemcpyAsync(out_stat, ctx->d_stat, sizeof(float) * 6 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_render_rgb8(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, uint8_t *out_rgb8,
+                             rt1w_render_stats *stats) {
+    if (!scene || !camera || !params || !out_rgb8) return fail(RT1W_ERR_INVALID, "null argument");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    if (params->width <= 0 || params->height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
+    if (params->flags & RT1W_FLAG_STATS) return fail(RT1W_ERR_INVALID, "RT1W_FLAG_STATS is only available through rt1w_render");
+    const size_t pixels = size_t(params->width) * size_t(params->height);
+    if (ctx->accum_pixels < pixels) {
+        cudaFree(ctx->d_accum), ctx->d_accum = nullptr, ctx->accum_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_accum), sizeof(float) * 3 * pixels));
+        ctx->accum_pixels = pixels;
+    }
+    if (ctx->rgb8_pixels < pixels) {
+        cudaFree(ctx->d_rgb8), ctx->d_rgb8 = nullptr, ctx->rgb8_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rgb8), 3 * pixels));
+        ctx->rgb8_pixels = pixels;
+    }
+    rt1w_status st = render_common(scene, camera, params, ctx->d_accum, nullptr, ctx->stream, stats);
+    if (st != RT1W_OK) return st;
+    RT1W_CUDA(resolve_launch(ctx->d_accum, 3 * pixels, params->sample_end - params->sample_begin, ctx->d_rgb8, ctx->stream));
+    RT1W_CUDA(cudaMemcpyAsync(out_rgb8, ctx->d_rgb8, 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
     RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
     return RT1W_OK;
 }

@@ -731,6 +731,27 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     return cudaSuccess;
 }
 
+// `Color::into_sampled` + `Display for SampledColor` (color.rs:14-21,56-65) on the device: NaN sum -> 0, mean, sqrt,
+// clamp to [0, 0.999], * 256, truncate; same f64 arithmetic as the host rt1w_resolve_rgb8 (bit-identical output).
+__global__ void __launch_bounds__(256) k_resolve(const float *__restrict__ rgb_sum, const size_t n, const double scale, uint8_t *__restrict__ out) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        double x = double(rgb_sum[i]);
+        if (x != x) x = 0.0;
+        x *= scale;
+        double g = sqrt(x);
+        g = g < 0.0 ? 0.0 : (g > 0.999 ? 0.999 : g);
+        const double q = 256.0 * g;
+        out[i] = q != q ? uint8_t(0) : uint8_t(int(q));
+    }
+}
+
+cudaError_t resolve_launch(const float *d_rgb_sum, size_t n_values, int samples_per_pixel, uint8_t *d_rgb8, cudaStream_t stream) {
+    if (n_values == 0) return cudaSuccess;
+    const size_t want = (n_values + 255) / 256;
+    k_resolve<<<int(want < 148 * 8 ? want : 148 * 8), 256, 0, stream>>>(d_rgb_sum, n_values, 1.0 / double(samples_per_pixel), d_rgb8);
+    return cudaGetLastError();
+}
+
 cudaError_t trace_closest_launch(const SceneView &sc, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, float *t,
                                  float *normal3, uint8_t *front_face, float *uv2, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;

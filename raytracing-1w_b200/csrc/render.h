@@ -69,4 +69,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
 cudaError_t trace_closest_launch(const SceneView &sc, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, float *t,
                                  float *normal3, uint8_t *front_face, float *uv2, cudaStream_t stream);
 
+// Device-side image resolve (color.rs:14-21,56-65): width*height*3 radiance sums -> 8-bit channels.
+cudaError_t resolve_launch(const float *d_rgb_sum, size_t n_values, int samples_per_pixel, uint8_t *d_rgb8, cudaStream_t stream);
+
 } // namespace rt1w

@@ -73,3 +73,18 @@ def test_product_does_not_link_the_oracle(rt):
     assert "oracle" not in out
     syms = subprocess.check_output(["nm", "-D", "--defined-only", rt.api.LIB_PATH], text=True)
     assert "oracle_" not in syms
+
+
+def test_demo_driver_fails_loudly_without_a_gpu(rt):
+    """rt1w_main (the reference's `main` on top of the C ABI) exists and has no CPU path either."""
+    import subprocess
+
+    import torch
+
+    exe = os.path.join(os.path.dirname(rt.api.LIB_PATH), "rt1w_main")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, "cornel_box", "--width", "8", "--spp", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "rt1w_context_create" in r.stderr
+    assert not r.stdout.startswith("P3")

@@ -40,6 +40,19 @@ BYTES_PER_PATH = 60.0       # generate write + accumulate
 METRIC = "Mpaths/s (Cornell box 600x600, 100 spp per GPU, depth 50)"
 
 
+def ncu_traffic():
+    """DRAM bytes of one steady-state k_wave launch (8.39 M work items) from the committed `ncu --set full` capture."""
+    try:
+        vals = {}
+        for line in open(os.path.join(ROOT, "profiles", "r01_wave_metrics.txt")):
+            k, v, *unit = line.split()
+            if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals[k] = float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit[0]]
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -123,8 +136,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-spp", type=int, default=4, help="samples per pixel of one reference-arm step")
-    ap.add_argument("--cpu-spp", type=int, default=8, help="samples per pixel of the cpu_baseline sample")
+    ap.add_argument("--ref-spp", type=int, default=8, help="samples per pixel of one reference-arm step")
+    ap.add_argument("--cpu-spp", type=int, default=32, help="samples per pixel of the cpu_baseline sample")
     ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -246,7 +259,9 @@ def main():
         alg_bytes = BYTES_PER_RAY * stp.rays + BYTES_PER_PATH * stp.paths  # all launches of one render
         achieved = alg_bytes / (wave_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_wave", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": which,
+                    "traffic": ncu_traffic(), "peak_source": which,
+                    "traffic_note": "ncu dram read+write of ONE steady-state launch (2^23 work items: 1.34e9 algorithmic bytes); "
+                                    "the per-launch average on the left includes the small launches of the tail",
                     "algorithmic_bytes_per_launch": alg_bytes / wave_n, "avg_launch_ms": wave_ms / wave_n,
                     "note": "148 B per ray segment + 60 B per path (SURVEY.md 8d) over all k_wave launches of one render; "
                             "the kernel moves 160 B per segment through HBM and is bound by instruction issue / latency, see DESIGN.md"}

@@ -821,63 +821,38 @@ RT1W_DEV f3 random_in_unit_sphere(Rng &rng) { // math.rs:6-18 (three gen_range(-
     }
 }
 
-RT1W_DEV f3 random_cosine_direction(float r1, float r2) { // math.rs:39-49
-    const float z = sqrtf(1.0f - r2);
-    float sn, cs;
-    sincospif(2.0f * r1, &sn, &cs);
-    const float q = sqrtf(r2);
-    return mk3(cs * q, sn * q, z);
-}
-
-RT1W_DEV f3 random_to_sphere(float radius, float distance_squared, float r1, float r2) { // math.rs:51-65
-    const float z = 1.0f + r2 * (sqrtf(1.0f - radius * radius / distance_squared) - 1.0f);
-    float sn, cs;
-    sincospif(2.0f * r1, &sn, &cs);
-    const float q = sqrtf(1.0f - z * z);
-    return mk3(cs * q, sn * q, z);
-}
-
 // pdf_value of one light for the ray (o, v), hit range [0.001, inf) (aarect.rs:119-138, sphere.rs:72-90).
+// f32 on coordinates taken relative to the light in f64 first: the hit test only decides pdf = 0 at the light's
+// silhouette, and the pdf value itself is an f32 quantity.
 RT1W_DEV float light_pdf_value(const DLight &L, double ox, double oy, double oz, f3 v) {
     if (L.kind == L_XZ_RECT) {
-        const double t = (L.p[4] - oy) / double(v.y);
-        if (t < kTMin || t > CUDART_INF) return 0.0f; // NaN passes both comparisons, as in aarect.rs:85-88
-        const double x = ox + t * double(v.x), z = oz + t * double(v.z);
-        if (x < L.p[0] || x > L.p[1] || z < L.p[2] || z > L.p[3]) return 0.0f;
-        const float area = float((L.p[1] - L.p[0]) * (L.p[3] - L.p[2]));
+        const float t = float(L.p[4] - oy) / v.y;
+        if (t < float(kTMin) || t > CUDART_INF_F) return 0.0f; // NaN passes both comparisons, as in aarect.rs:85-88
+        const float x = float(ox - L.p[0]) + t * v.x, z = float(oz - L.p[2]) + t * v.z;
+        const float wx = float(L.p[1] - L.p[0]), wz = float(L.p[3] - L.p[2]);
+        if (x < 0.0f || x > wx || z < 0.0f || z > wz) return 0.0f;
         const float len2 = dot(v, v);
-        const float tf = float(t);
-        const float distance_squared = tf * tf * len2;
+        const float distance_squared = t * t * len2;
         const float cosine = fabsf(v.y * rsqrtf(len2)); // normal is +-y
-        return distance_squared / (cosine * area);
+        return distance_squared / (cosine * (wx * wz));
     }
-    if (L.kind == L_SPHERE) {
-        LocalRay l;
-        l.ox = ox, l.oy = oy, l.oz = oz, l.dx = v.x, l.dy = v.y, l.dz = v.z;
-        double t;
-        if (!hit_sphere(l, L.p[0], L.p[1], L.p[2], L.p[3], kTMin, CUDART_INF, t)) return 0.0f;
-        const double cx = L.p[0] - ox, cy = L.p[1] - oy, cz = L.p[2] - oz;
-        const float d2 = float(cx * cx + cy * cy + cz * cz);
+    if (L.kind == L_SPHERE) { // sphere.rs:24-48 with co = centre - origin
+        const f3 co = mk3(float(L.p[0] - ox), float(L.p[1] - oy), float(L.p[2] - oz));
         const float r = float(L.p[3]);
+        const float a = dot(v, v), cv = dot(co, v), d2 = dot(co, co);
+        const float disc = cv * cv - a * (d2 - r * r);
+        if (disc < 0.0f) return 0.0f;
+        const float sq = sqrtf(disc), inv_a = 1.0f / a;
+        float root = (cv - sq) * inv_a;
+        if (root < float(kTMin) || root > CUDART_INF_F) {
+            root = (cv + sq) * inv_a;
+            if (root < float(kTMin) || root > CUDART_INF_F) return 0.0f;
+        }
         const float cos_theta_max = sqrtf(1.0f - r * r / d2);
         const float solid_angle = 2.0f * kPiF * (1.0f - cos_theta_max);
         return 1.0f / solid_angle;
     }
     return 0.0f; // trait default, hittable.rs:66-68
-}
-
-RT1W_DEV f3 light_random(const DLight &L, double ox, double oy, double oz, float r1, float r2) {
-    if (L.kind == L_XZ_RECT) { // aarect.rs:140-147 (un-normalised)
-        const double x = L.p[0] + (L.p[1] - L.p[0]) * double(r1);
-        const double z = L.p[2] + (L.p[3] - L.p[2]) * double(r2);
-        return mk3(float(x - ox), float(L.p[4] - oy), float(z - oz));
-    }
-    if (L.kind == L_SPHERE) { // sphere.rs:92-99
-        const f3 dir = mk3(float(L.p[0] - ox), float(L.p[1] - oy), float(L.p[2] - oz));
-        const Onb uvw = onb_from_w(dir);
-        return onb_local(uvw, random_to_sphere(float(L.p[3]), dot(dir, dir), r1, r2));
-    }
-    return mk3(1.0f, 0.0f, 0.0f); // trait default, hittable.rs:69-71
 }
 
 // ------------------------------------------------------------------------------------------
@@ -901,31 +876,49 @@ RT1W_DEV float reflectance(float cosine, float ref_idx) { // material.rs:121-125
     return r0 + (1.0f - r0) * (m2 * m2 * m);
 }
 
-// Lambertian + MixturePdf(HittablePdf(lights), CosinePdf) — main.rs:75-104 / :142-160, material.rs:70-92, pdf.rs:36-69
+// Lambertian + MixturePdf(HittablePdf(lights), CosinePdf) — main.rs:75-104 / :142-160, material.rs:70-92, pdf.rs:36-69.
+// A cosine sample (math.rs:39-49) and a sample towards a sphere light (math.rs:51-65, sphere.rs:92-99) are both
+// `onb.local(cos(phi) q, sin(phi) q, z)` with q = sqrt(1 - z^2), about the normal resp. the direction to the
+// sphere, so the two strategies share one code path; a rectangle light (aarect.rs:140-147) is the short branch.
 RT1W_DEV f3 scatter_lambertian(const SceneView &sc, const DLight *lights, const HitInfo &h, Rng &rng, f3 &weight) {
-    const Onb uvw = onb_from_w(h.normal);
+    const f3 w = normalize(h.normal); // onb.rs:14
     const Philox4 x = rng.next4();
-    f3 dir;
-    float pdf;
-    if (sc.has_lights) {
-        const int n = sc.n_lights;
-        if (x.x >> 31) { // rng.gen::<bool>() -> HittablePdf (pdf.rs:63-64)
-            const int pick = min(int(u01(x.y) * float(n)), n - 1); // slice.choose (hittable.rs:153)
-            dir = light_random(lights[pick], h.px, h.py, h.pz, u01(x.z), u01(x.w));
-        } else {
-            dir = onb_local(uvw, random_cosine_direction(u01(x.z), u01(x.w)));
+    const float r1 = u01(x.z), r2 = u01(x.w);
+    f3 dir, axis = w;
+    float z = sqrtf(1.0f - r2);
+    bool local = true; // the direction comes out of an ONB
+    const int n = sc.has_lights ? sc.n_lights : 0;
+    if (n > 0 && (x.x >> 31)) { // rng.gen::<bool>() -> HittablePdf (pdf.rs:63-64)
+        const DLight &L = lights[min(int(u01(x.y) * float(n)), n - 1)]; // slice.choose (hittable.rs:153)
+        if (L.kind == L_XZ_RECT) { // un-normalised
+            const double px = L.p[0] + (L.p[1] - L.p[0]) * double(r1), pz = L.p[2] + (L.p[3] - L.p[2]) * double(r2);
+            dir = mk3(float(px - h.px), float(L.p[4] - h.py), float(pz - h.pz));
+            local = false;
+        } else if (L.kind == L_SPHERE) {
+            axis = mk3(float(L.p[0] - h.px), float(L.p[1] - h.py), float(L.p[2] - h.pz));
+            const float radius = float(L.p[3]);
+            z = 1.0f + r2 * (sqrtf(1.0f - radius * radius / dot(axis, axis)) - 1.0f);
+        } else { // trait default, hittable.rs:69-71
+            dir = mk3(1.0f, 0.0f, 0.0f);
+            local = false;
         }
+    }
+    if (local) {
+        const Onb uvw = onb_from_w(axis);
+        float sn, cs;
+        sincospif(2.0f * r1, &sn, &cs);
+        const float q = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        dir = onb_local(uvw, mk3(cs * q, sn * q, z));
+    }
+    const float cosine = dot(normalize(dir), w) * (1.0f / kPiF); // pdf.rs:37-40 and material.rs:82-91 (same expression)
+    float pdf = fmaxf(cosine, 0.0f);
+    if (n > 0) {
         float lsum = 0.0f;
         const float wl = 1.0f / float(n);
         for (int i = 0; i < n; ++i) lsum += wl * light_pdf_value(lights[i], h.px, h.py, h.pz, dir); // hittable.rs:144-150
-        const float cosine = dot(normalize(dir), uvw.w);
-        pdf = 0.5f * lsum + 0.5f * fmaxf(cosine * (1.0f / kPiF), 0.0f); // pdf.rs:58-60
-    } else {
-        dir = onb_local(uvw, random_cosine_direction(u01(x.z), u01(x.w)));
-        pdf = fmaxf(dot(normalize(dir), uvw.w) * (1.0f / kPiF), 0.0f); // pdf.rs:37-40
+        pdf = 0.5f * lsum + 0.5f * pdf; // pdf.rs:58-60
     }
-    const float spdf = fmaxf(dot(h.normal, normalize(dir)) * (1.0f / kPiF), 0.0f); // material.rs:82-91
-    const float s = spdf / pdf;                                                      // unguarded, main.rs:102
+    const float s = fmaxf(cosine, 0.0f) / pdf; // unguarded, main.rs:102
     weight = mk3(s, s, s);
     return dir;
 }

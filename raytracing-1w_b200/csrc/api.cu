@@ -11,6 +11,7 @@
 
 #include "../../include/rt1w.h"
 #include "bvh.h"
+#include "lbvh.h"
 #include "lower.h"
 #include "render.h"
 
@@ -36,6 +37,7 @@ rt1w_status fail_cuda(const char *what, cudaError_t e) {
     } while (0)
 
 constexpr uint32_t kDefaultPool = 1u << 23; // rays in flight per wave: the queues stream through HBM, so bigger waves amortise launches and the tail
+constexpr int kLbvhFromPrims = 1 << 17;      // scenes from this many primitives on get their BVH built on the device
 constexpr int kMaxLeaf = 1; // single-primitive leaves: the f32 leaf-box test screens the f64 primitive solve
 
 // Bounds of a lowered primitive in its own frame (the box its wrapper chain rotates and translates).
@@ -226,8 +228,34 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
             if (!std::isfinite(bmin[3 * i + k]) || !std::isfinite(bmax[3 * i + k]))
                 return fail(RT1W_ERR_INVALID, "No bounding box in bvh_node constructor. (bvh.rs:65-67): non-finite primitive bounds");
         }
+    // Builder: binned SAH on the host (best trees; seconds for a million primitives) or, for big scenes, a linear BVH
+    // on the device (lbvh.cu; milliseconds).  RT1W_BVH_BUILDER=sah|lbvh overrides the size rule (tuning, tests).
     BvhBuildResult bvh;
-    build_sah_bvh(bmin.data(), bmax.data(), n, kMaxLeaf, bvh);
+    BvhNode32 *d_lbvh_nodes = nullptr;
+    size_t n_bvh_nodes = 0;
+    bool use_lbvh = n >= size_t(kLbvhFromPrims);
+    if (const char *env = std::getenv("RT1W_BVH_BUILDER")) use_lbvh = std::strcmp(env, "lbvh") == 0 ? n >= 2 : (std::strcmp(env, "sah") == 0 ? false : use_lbvh);
+    if (use_lbvh) {
+        RT1W_CUDA(cudaSetDevice(ctx->device));
+        std::vector<float> boxes(6 * n);
+        for (size_t i = 0; i < n; ++i) conservative_box(dev[i].bbox_min, dev[i].bbox_max, &boxes[6 * i], &boxes[6 * i + 3]);
+        int depth = 0;
+        cudaError_t e = build_lbvh(boxes.data(), n, ctx->stream, &d_lbvh_nodes, &n_bvh_nodes, bvh.prim_order, &depth);
+        if (e != cudaSuccess) return fail_cuda("device BVH build", e);
+        bvh.depth = depth;
+        if (depth > kStackSmem + kStackLocal - 2) { // many coincident centroids: let the SAH builder split by index instead
+            cudaFree(d_lbvh_nodes), d_lbvh_nodes = nullptr;
+            use_lbvh = false;
+        }
+    }
+    if (!use_lbvh) {
+        build_sah_bvh(bmin.data(), bmax.data(), n, kMaxLeaf, bvh);
+        n_bvh_nodes = bvh.nodes.size();
+    }
+    struct NodeGuard { // the device nodes belong to the scene once it exists
+        BvhNode32 *&p;
+        ~NodeGuard() { cudaFree(p); }
+    } node_guard{d_lbvh_nodes};
     if (bvh.depth > kStackSmem + kStackLocal - 2) return fail(RT1W_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
     std::vector<DPrim> dprims(n);
     std::vector<int32_t> prim_id(n);
@@ -291,8 +319,12 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     std::unique_ptr<rt1w_scene, void (*)(rt1w_scene *)> s(new rt1w_scene(), scene_release);
     s->ctx = ctx;
     static_assert(sizeof(BvhNode32) == 2 * sizeof(float4), "node layout");
-    RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
-    RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
+    if (d_lbvh_nodes) {
+        s->d_nodes = reinterpret_cast<float4 *>(d_lbvh_nodes), d_lbvh_nodes = nullptr;
+    } else {
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
+        RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
+    }
     RT1W_CUDA(upload(dprims, &s->d_prims));
     RT1W_CUDA(upload(prim_boxes, &s->d_prim_boxes));
     RT1W_CUDA(upload(prim_id, &s->d_prim_id));
@@ -335,11 +367,11 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     v.materials = s->d_materials, v.textures = s->d_textures, v.perlins = s->d_perlins;
     v.images = s->d_images, v.image_dims = s->d_image_dims, v.lights = s->d_lights;
     v.n_lights = int32_t(low.lights.size()), v.has_lights = low.has_lights ? 1 : 0;
-    v.n_prims = int32_t(n), v.n_nodes = int32_t(bvh.nodes.size()), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
+    v.n_prims = int32_t(n), v.n_nodes = int32_t(n_bvh_nodes), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
     v.flat = flat ? 1 : 0;
     s->material_mask = low.material_mask;
     s->prims = low.prims;
-    s->info.n_prims = int32_t(low.prims.size()), s->info.n_bvh_nodes = int32_t(bvh.nodes.size()), s->info.n_frames = int32_t(low.frames.size());
+    s->info.n_prims = int32_t(low.prims.size()), s->info.n_bvh_nodes = int32_t(n_bvh_nodes), s->info.n_frames = int32_t(low.frames.size());
     s->info.n_lights = int32_t(low.lights.size()), s->info.bvh_depth = bvh.depth, s->info.material_mask = low.material_mask;
     s->info.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     s->info.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();

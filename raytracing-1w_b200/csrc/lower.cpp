@@ -113,6 +113,10 @@ struct Walker {
 
     // world-space bounds of a local box under the current chain
     void world_bounds(const double lmin[3], const double lmax[3], double wmin[3], double wmax[3]) const {
+        if (!chain_has_transform()) { // the common case (a million bare spheres): nothing to compose
+            for (int k = 0; k < 3; ++k) wmin[k] = lmin[k], wmax[k] = lmax[k];
+            return;
+        }
         Xform x;
         for (auto &w : chain) {
             if (w.kind == OP_TRANSLATE) {
@@ -370,6 +374,7 @@ rt1w_status lower_scene(const rt1w_scene_desc *desc, LoweredScene &out, std::str
         if (!desc) throw Fail(RT1W_ERR_INVALID, "null scene description");
         if (desc->n_nodes <= 0 || !desc->nodes) throw Fail(RT1W_ERR_INVALID, "empty scene (objects mut not be empty, bvh.rs:61)");
         lower_tables(*desc, out);
+        out.prims.reserve(size_t(desc->n_nodes));
         Walker w{*desc, out};
         w.walk(desc->world);
         if (out.prims.empty()) throw Fail(RT1W_ERR_INVALID, "scene has no primitives");

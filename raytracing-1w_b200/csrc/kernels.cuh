@@ -453,6 +453,10 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
 //   pass 2 (per lane, f64): solve the nearest candidate, then the nearest remaining one whose box is entered
 //     before the best hit so far (the entry distance is a lower bound of the primitive's t), and so on:
 //     ~1.2 solves per ray.
+#ifndef RT1W_SCAN_UNROLL
+#define RT1W_SCAN_UNROLL 4
+#endif
+constexpr int kScanUnroll = RT1W_SCAN_UNROLL;
 constexpr int kFlatMax = 32;
 constexpr int kFlatMaxFrames = 8;
 
@@ -546,21 +550,25 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
     const int n_groups = fs.n_groups;
     int k = 0, cur_frame = -2;
     SlabRayF s;
-    f3 o, d;
     for (int g = 0; g < n_groups; ++g) {
         const int frame = fs.group_frame[g], end = fs.group_end[g];
         if (frame != cur_frame) {
             cur_frame = frame;
             if (frame < 0) {
                 s = slab_ray(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
-                o = mk3(float(r.ox), float(r.oy), float(r.oz)), d = mk3(r.dx, r.dy, r.dz);
             } else {
                 const LocalRay l = to_local(frame_xf(fs.frames, frame), r);
                 s = slab_ray(l.ox, l.oy, l.oz, float(l.dx), float(l.dy), float(l.dz));
-                o = mk3(float(l.ox), float(l.oy), float(l.oz)), d = mk3(float(l.dx), float(l.dy), float(l.dz));
             }
         }
         if (fs.group_sphere[g]) {
+            f3 o, d; // the ray in the group's frame, f32
+            if (frame < 0) {
+                o = mk3(float(r.ox), float(r.oy), float(r.oz)), d = mk3(r.dx, r.dy, r.dz);
+            } else {
+                const LocalRay l = to_local(frame_xf(fs.frames, frame), r);
+                o = mk3(float(l.ox), float(l.oy), float(l.oz)), d = mk3(float(l.dx), float(l.dy), float(l.dz));
+            }
             for (; k < end; ++k, bit <<= 1) {
                 float tn;
                 const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn) && sphere_maybe(fs.sphere[k], o, d);
@@ -569,6 +577,7 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
                 if (in && tn < t1) t1 = tn, k1 = k;
             }
         } else {
+#pragma unroll(kScanUnroll)
             for (; k < end; ++k, bit <<= 1) {
                 float tn;
                 const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn) && (bit & keep) != 0u;

@@ -52,6 +52,7 @@ struct SceneView {
     int32_t n_lights, has_lights;
     int32_t n_prims, n_nodes, n_perlins, n_frames;
     int32_t flat; // scan the primitive list (closest_hit_flat) instead of walking the BVH
+    int32_t rich_textures; // some texture is not a SolidColor
 };
 
 struct f3 {
@@ -770,8 +771,10 @@ RT1W_DEV float sin_reduced(double x) {
 }
 
 // `perlins` may point at shared memory copies of the tables (render.cu stages them per CTA).
-RT1W_DEV_BIG f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
+// RICH = false: the scene has only SolidColor textures (checker, Perlin and image code compiled out).
+template <bool RICH> RT1W_DEV_BIG f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
     DTexture t = sc.textures[tex];
+    if (!RICH) return mk3(t.color[0], t.color[1], t.color[2]);
     for (int guard = 0; guard < 9 && t.type == RT1W_TEX_CHECKER; ++guard) { // texture.rs:46-55
         const float sines = sin_reduced(10.0 * h.px) * sin_reduced(10.0 * h.py) * sin_reduced(10.0 * h.pz);
         t = sc.textures[sines < 0.0f ? t.odd : t.even];

@@ -33,7 +33,7 @@ namespace rt1w {
 #define RT1W_WAVE_THREADS 128
 #endif
 #ifndef RT1W_FLAT_MIN_BLOCKS
-#define RT1W_FLAT_MIN_BLOCKS 5
+#define RT1W_FLAT_MIN_BLOCKS 5 // CTAs per SM of the flat-scan wave kernel with media; one more (80 registers, no spills) without
 #endif
 #ifndef RT1W_BVH_MIN_BLOCKS
 #define RT1W_BVH_MIN_BLOCKS 4
@@ -152,14 +152,16 @@ RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t s0, uint32_t p0, uint32_
 }
 
 // ------------------------------------------------------------------------------------------
-// scatter at a queued hit: one instantiation per scattering material family.  Rewrites `r` into the
+// scatter at a queued hit of material family `mat` (warp-uniform in the wave kernels).  Rewrites `r` into the
 // scattered ray, advances the depth in c.state and folds the attenuation into `thr`.  Returns false when
-// the path ends here (depth limit, main.rs:59-61).
+// the path ends here (depth limit, main.rs:59-61).  One copy of the hit reconstruction, the Philox setup and the
+// epilogue serves all families: instruction-cache footprint is what the wave kernel is most sensitive to.
 // ------------------------------------------------------------------------------------------
 // `prims`, `frames`: the scene tables (global memory, or the flat scan's shared-memory copies).
-template <int MAT>
-RT1W_DEV bool scatter(const RenderArgs &a, const DPrim *prims, const DFrame *frames, const DPerlin *perlins, const DLight *lights, Ray &r,
-                      const HitRec &hr, RayC &c, f3 &thr) {
+// MEDIA = false: no Isotropic hits can be queued (ConstantMedium::new is the only source, constant_medium.rs:22-28).
+template <bool MEDIA, bool RICH>
+RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, const DFrame *frames, const DPerlin *perlins, const DLight *lights,
+                      Ray &r, const HitRec &hr, RayC &c, f3 &thr) {
     const DMaterial m = a.sc.materials[hr.meta >> 12];
     const HitInfo h = finalize_hit<false>(prims + (hr.leaf & kLeafMask), frames, hr.leaf >> kLeafBits, r, hr.t);
     const uint32_t depth = c.state & 255u;
@@ -168,25 +170,22 @@ RT1W_DEV bool scatter(const RenderArgs &a, const DPrim *prims, const DFrame *fra
     rng.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), rng.c1 = depth, rng.c2 = purpose_word(a.rp, RNG_SCATTER), rng.block = 0;
     f3 dir;
     float time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
-    if (MAT == RT1W_MAT_LAMBERTIAN) {
-        const f3 att = texture_value(a.sc, perlins, m.texture, h);
+    if (mat == RT1W_MAT_LAMBERTIAN) {
+        const f3 att = texture_value<RICH>(a.sc, perlins, m.texture, h);
         f3 weight;
         dir = scatter_lambertian(a.sc, lights, h, rng, weight);
         thr = thr * att * weight;
         time = float(hr.t); // main.rs:86,145: the scattered ray's time is the hit parameter t
-    } else if (MAT == RT1W_MAT_METAL) {
+    } else if (mat == RT1W_MAT_METAL) {
         dir = scatter_metal(m, r, h, rng);
         thr = thr * mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
-    } else if (MAT == RT1W_MAT_DIELECTRIC) {
+    } else if (mat == RT1W_MAT_DIELECTRIC || !MEDIA) {
         dir = scatter_dielectric(m, r, h, rng); // attenuation (1,1,1)
     } else {                                    // Isotropic, constant_medium.rs:36-51
-        thr = thr * texture_value(a.sc, perlins, m.texture, h);
+        thr = thr * texture_value<RICH>(a.sc, perlins, m.texture, h);
         dir = random_in_unit_sphere(rng);
     }
-    if (depth + 1u >= uint32_t(a.rp.max_depth)) { // main.rs:59-61: the next ray_color call returns black
-        if (!finite3(thr)) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
-        return false;
-    }
+    if (depth + 1u >= uint32_t(a.rp.max_depth)) return false; // main.rs:59-61: the next ray_color call returns black (the caller keeps a NaN throughput alive in the pixel)
     r.ox = h.px, r.oy = h.py, r.oz = h.pz;
     r.dx = dir.x, r.dy = dir.y, r.dz = dir.z;
     r.time = time;
@@ -199,11 +198,12 @@ RT1W_DEV bool scatter(const RenderArgs &a, const DPrim *prims, const DFrame *fra
 // ------------------------------------------------------------------------------------------
 // FLAT: scan the primitive list staged in shared memory (small scenes) instead of walking the BVH.
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
-template <bool FLAT, bool MEDIA>
+// RICH: some texture is not a SolidColor (else checker / Perlin / image code is compiled out: a third of the kernel).
+template <bool FLAT, bool MEDIA, bool RICH>
 #ifdef RT1W_REGS_FROM_FLAG // sweeps: register budget from --maxrregcount instead of the launch bounds
 __global__ void
 #else
-__global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS)
+__global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BLOCKS : RT1W_FLAT_MIN_BLOCKS + 1) : RT1W_BVH_MIN_BLOCKS)
 #endif
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
     }
     if (FLAT) flat_stage(a.sc, s_flat[0]);
     const DPerlin *perlins = a.sc.perlins;
-    if (perlin_in_smem) {
+    if (RICH && perlin_in_smem) {
         const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
         uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
@@ -264,15 +264,14 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
     const DPrim *prims = FLAT ? s_flat[0].prims : a.sc.prims;
     const DFrame *frames = FLAT ? s_flat[0].frames : a.sc.frames;
     const volatile Layout &lay = s_layout;
-    const bool has_background = a.rp.background[0] != 0.0f || a.rp.background[1] != 0.0f || a.rp.background[2] != 0.0f;
     uint32_t traced = 0;
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < lay.total; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;
         Ray r;
         RayC c;
         f3 thr;
-        bool alive = false;
-        int skip_leaf = -1; // the primitive the ray starts on
+        bool alive = false, ends = false; // ends: the path is over and its pixel gets throughput * rad
+        int skip_leaf = -1;               // the primitive the ray starts on
         const uint32_t off4 = lay.off4;
         if (i < off4) { // a hit queued by the previous wave: scatter
             const uint32_t off1 = lay.off1, off2 = lay.off2, off3 = lay.off3;
@@ -285,10 +284,8 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
                 skip_leaf = hr.leaf;
                 const float4 th4 = in.t[j];
                 thr = mk3(th4.x, th4.y, th4.z);
-                if (seg == 0) alive = scatter<RT1W_MAT_LAMBERTIAN>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
-                else if (seg == 1) alive = scatter<RT1W_MAT_METAL>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
-                else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
-                else alive = scatter<RT1W_MAT_ISOTROPIC>(a, prims, frames, perlins, s_lights, r, hr, c, thr);
+                alive = scatter<MEDIA, RICH>(scatter_mat(seg), a, prims, frames, perlins, s_lights, r, hr, c, thr);
+                ends = !alive; // depth limit: zero radiance
             }
         } else if (i < lay.total) { // a new camera path
             r = generate_ray(a, lay.gen_s0, lay.gen_p0, i - off4, c.state, c.pixel);
@@ -298,6 +295,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
 
         int dest = -1;
         HitRec h;
+        f3 rad = mk3(0.0f, 0.0f, 0.0f); // radiance the path ends on
         if (alive) { // extend: closest hit, then end the path or hand it to the material it landed on
             ++traced;
             MediumRng mr = {0, 0, 0, 0, 0};
@@ -314,15 +312,17 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? RT1W_FLAT_MIN_BLOCKS : RT
             }
             if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
                 const HitInfo hi = finalize_hit<false>(prims + (h.leaf & kLeafMask), frames, h.leaf >> kLeafBits, r, h.t);
-                const f3 e = hi.front_face ? texture_value(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
-                splat(a, c.pixel, thr, e);
+                if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
+                ends = true;
             } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
-                const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
-                if (has_background || !finite3(thr)) splat(a, c.pixel, thr, rad);
+                if (!hit) rad = mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
+                ends = true;
             } else {
                 dest = mat_type;
             }
         }
+        // the one place a path reaches its pixel; zero radiance still has to deliver a NaN / inf throughput (splat)
+        if (ends && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f || !finite3(thr))) splat(a, c.pixel, thr, rad);
         __syncwarp();
         const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
         if (dest >= 0) { // ray + path state + hit go to the queue of the material the ray landed on
@@ -470,10 +470,8 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
                         const HitRec hr = in.h[j];
                         const float4 th4 = in.t[j];
                         nthr = mk3(th4.x, th4.y, th4.z);
-                        if (seg == 0) alive = scatter<RT1W_MAT_LAMBERTIAN>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
-                        else if (seg == 1) alive = scatter<RT1W_MAT_METAL>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
-                        else if (seg == 2) alive = scatter<RT1W_MAT_DIELECTRIC>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
-                        else alive = scatter<RT1W_MAT_ISOTROPIC>(a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                        alive = scatter<MEDIA, true>(scatter_mat(seg), a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                        if (!alive && !finite3(nthr)) splat(a, nc.pixel, nthr, mk3(0.0f, 0.0f, 0.0f)); // depth limit: a NaN throughput still reaches the pixel
                     }
                 } else if (i < lay.total) { // a new camera path
                     nr = generate_ray(a, lay.gen_s0, lay.gen_p0, i - off4, nc.state, nc.pixel);
@@ -542,7 +540,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
                 }
                 if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
                     const HitInfo hi = finalize_hit<false>(a.sc.prims + (h.leaf & kLeafMask), a.sc.frames, h.leaf >> kLeafBits, r, h.t);
-                    const f3 e = hi.front_face ? texture_value(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
+                    const f3 e = hi.front_face ? texture_value<true>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
                     splat(a, c.pixel, thr, e);
                 } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
                     const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
@@ -670,9 +668,11 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     bool persistent = args.sc.n_nodes > kPersistentFromNodes;
     if (args.rp.flags & RT1W_FLAG_BVH_LOCKSTEP) persistent = false;
     if (args.rp.flags & RT1W_FLAG_BVH_PERSISTENT) persistent = true;
-    const WaveKernel kernel = flat         ? (media ? k_wave<true, true> : k_wave<true, false>)
+    const bool rich = args.sc.rich_textures != 0;
+    const WaveKernel kernel = flat ? (media ? (rich ? k_wave<true, true, true> : k_wave<true, true, false>)
+                                            : (rich ? k_wave<true, false, true> : k_wave<true, false, false>))
                               : persistent ? (media ? k_wave_bvh<true> : k_wave_bvh<false>)
-                                           : (media ? k_wave<false, true> : k_wave<false, false>);
+                                           : (media ? k_wave<false, true, true> : k_wave<false, false, true>);
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWaveThreads, perlin_bytes)) != cudaSuccess) return e;

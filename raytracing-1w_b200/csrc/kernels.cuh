@@ -772,7 +772,7 @@ RT1W_DEV float sin_reduced(double x) {
 
 // `perlins` may point at shared memory copies of the tables (render.cu stages them per CTA).
 // RICH = false: the scene has only SolidColor textures (checker, Perlin and image code compiled out).
-template <bool RICH> RT1W_DEV_BIG f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
+template <bool RICH> RT1W_DEV f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
     DTexture t = sc.textures[tex];
     if (!RICH) return mk3(t.color[0], t.color[1], t.color[2]);
     for (int guard = 0; guard < 9 && t.type == RT1W_TEX_CHECKER; ++guard) { // texture.rs:46-55

@@ -458,6 +458,9 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
 #define RT1W_SCAN_UNROLL 4
 #endif
 constexpr int kScanUnroll = RT1W_SCAN_UNROLL;
+#ifdef RT1W_COUNT_SOLVES // measurement build (build.py --variant count -DRT1W_COUNT_SOLVES): rays, pass-1 candidates, f64 solves, warp-level solve iterations
+static __device__ unsigned long long g_scan_counts[4];
+#endif
 constexpr int kFlatMax = 32;
 constexpr int kFlatMaxFrames = 8;
 
@@ -592,7 +595,14 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
     float bestf = CUDART_INF_F;
     int best_leaf = -1;
     k = k1;
+#ifdef RT1W_COUNT_SOLVES
+    atomicAdd(&g_scan_counts[0], 1ull), atomicAdd(&g_scan_counts[1], (unsigned long long)__popc(cand));
+#endif
     while (k >= 0) {
+#ifdef RT1W_COUNT_SOLVES
+        atomicAdd(&g_scan_counts[2], 1ull);
+        if (int(threadIdx.x & 31) == __ffs(int(__activemask())) - 1) atomicAdd(&g_scan_counts[3], 1ull);
+#endif
         cand &= ~(1u << k);
         const int leaf = __float_as_int(fs.lo[k].w);
         double t;

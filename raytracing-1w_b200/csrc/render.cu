@@ -728,6 +728,15 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     if (e != cudaSuccess) return e;
     ws.waves = wave;
     ws.rays = h_ctr->rays;
+#ifdef RT1W_COUNT_SOLVES
+    if (flat) {
+        unsigned long long d[4] = {0, 0, 0, 0}, zero[4] = {0, 0, 0, 0};
+        cudaMemcpyFromSymbol(d, g_scan_counts, sizeof(d));
+        cudaMemcpyToSymbol(g_scan_counts, zero, sizeof(zero));
+        std::fprintf(stderr, "[flat scan] rays %llu, candidates per ray %.3f, f64 solves per ray %.3f, solve iterations per warp of 32 rays %.3f\n", d[0],
+                     double(d[1]) / double(d[0]), double(d[2]) / double(d[0]), 32.0 * double(d[3]) / double(d[0]));
+    }
+#endif
     return cudaSuccess;
 }
 

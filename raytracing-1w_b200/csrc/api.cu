@@ -152,7 +152,7 @@ rt1w_status rt1w_context_create(int32_t device_id, rt1w_context **out) {
     RT1W_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     RT1W_CUDA(cudaEventCreate(&ctx->ev0));
     RT1W_CUDA(cudaEventCreate(&ctx->ev1));
-    RT1W_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_ctr), sizeof(Counters)));
+    RT1W_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_ctr), 2 * sizeof(Counters))); // two snapshots: the poll runs one chunk behind
     *out = ctx.release();
     return RT1W_OK;
 }

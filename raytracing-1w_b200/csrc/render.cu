@@ -704,8 +704,20 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         marks.clear();
     };
 
-    uint64_t wave = 0;
-    for (;;) {
+    // Termination poll, one chunk behind: the counters after chunk c are copied to a pinned snapshot while chunk
+    // c + 1 is already queued, so the GPU never idles waiting for the host.  The price is one chunk of empty waves
+    // (a few microseconds each) after the last useful one.
+    auto finished = [&](const Counters &c, uint64_t next_wave) { // what wave `next_wave` would see: no path left to start, no hit queued
+        const int slot = int(next_wave % 3);
+        uint32_t queued = 0;
+        for (int q = 0; q < Q_COUNT; ++q) queued += c.n_mat[slot][q];
+        return c.next_path[slot] >= args.rp.total_paths && queued == 0;
+    };
+    cudaEvent_t snap_ev[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&snap_ev[k], cudaEventDisableTiming);
+    uint64_t wave = 0, chunk = 0;
+    const Counters *last = h_ctr;
+    while (e == cudaSuccess) {
         for (int k = 0; k < poll_every; ++k, ++wave) {
             const int slot = int(wave % 3), parity = int(wave & 1);
             mark(K_WAVE);
@@ -713,21 +725,33 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
             ++ws.launches;
         }
         mark(-1);
+        Counters *snap = h_ctr + (chunk & 1);
         if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(h_ctr, args.pool.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) break;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) break;
-        drain_marks();
-        // what wave `wave` would see: no path left to start and no hit queued
-        const int slot = int(wave % 3);
-        uint32_t queued = 0;
-        for (int q = 0; q < Q_COUNT; ++q) queued += h_ctr->n_mat[slot][q];
-        if (h_ctr->next_path[slot] >= args.rp.total_paths && queued == 0) break;
+        if ((e = cudaMemcpyAsync(snap, args.pool.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) break;
+        if ((e = cudaEventRecord(snap_ev[chunk & 1], stream)) != cudaSuccess) break;
+        if (ws.profile) { // per-launch event times are read chunk by chunk
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) break;
+            drain_marks();
+            last = snap;
+            if (finished(*snap, wave)) break;
+        } else if (chunk >= 1) {
+            const Counters *prev = h_ctr + ((chunk - 1) & 1);
+            if ((e = cudaEventSynchronize(snap_ev[(chunk - 1) & 1])) != cudaSuccess) break;
+            if (finished(*prev, wave - poll_every)) {
+                e = cudaStreamSynchronize(stream); // the chunk queued meanwhile ran on empty queues
+                last = snap;
+                break;
+            }
+        }
+        ++chunk;
     }
+    for (int k = 0; k < 2; ++k)
+        if (snap_ev[k]) cudaEventDestroy(snap_ev[k]);
     for (auto &m : marks) cudaEventDestroy(m.ev);
     for (auto ev : spare) cudaEventDestroy(ev);
     if (e != cudaSuccess) return e;
     ws.waves = wave;
-    ws.rays = h_ctr->rays;
+    ws.rays = last->rays;
 #ifdef RT1W_COUNT_SOLVES
     if (flat) {
         unsigned long long d[4] = {0, 0, 0, 0}, zero[4] = {0, 0, 0, 0};

@@ -62,7 +62,7 @@ struct WaveStats {
 
 // Runs the wave loop to completion on `stream` (accum/stat must be zeroed by the caller).
 // material_mask: bit m set when some primitive uses rt1w_material_type m.
-// h_ctr: pinned host mirror of the counters used for the termination poll.
+// h_ctr: TWO pinned host snapshots of the counters (the termination poll runs one chunk of waves behind).
 cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_ctr, cudaStream_t stream, int sm_count, WaveStats &ws);
 
 // Closest-hit parity kernel (rt1w_trace_closest).  All pointers are device pointers; outputs may be null.

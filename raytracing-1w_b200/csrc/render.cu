@@ -94,10 +94,22 @@ RT1W_DEV void splat(const RenderArgs &a, uint32_t seed, f3 thr, f3 radiance) {
 }
 RT1W_DEV bool finite3(f3 v) { return (fabsf(v.x) + fabsf(v.y) + fabsf(v.z)) < CUDART_INF_F; } // false for NaN and inf
 
+// Queue entries are read once and written once per wave: streaming (evict-first) accesses keep them from
+// pushing the radiance sums and the scene out of L2.
+template <class T> RT1W_DEV T stream_load(const T *p) {
+    static_assert(sizeof(T) == 16, "queue arrays hold 16-byte elements");
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
+    return *reinterpret_cast<const T *>(&v);
+}
+template <class T> RT1W_DEV void stream_store(T *p, const T &x) {
+    static_assert(sizeof(T) == 16, "queue arrays hold 16-byte elements");
+    __stcs(reinterpret_cast<float4 *>(p), *reinterpret_cast<const float4 *>(&x));
+}
+
 RT1W_DEV Ray load_ray(const RayQueue &q, uint32_t i, RayC &c) {
-    const double2 a = q.a[i];
-    const RayB b = q.b[i];
-    c = q.c[i];
+    const double2 a = stream_load(q.a + i);
+    const RayB b = stream_load(q.b + i);
+    c = stream_load(q.c + i);
     Ray r;
     r.ox = a.x, r.oy = a.y, r.oz = b.oz;
     r.dx = b.dx, r.dy = b.dy, r.dz = c.dz;
@@ -280,9 +292,9 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BL
             if (j < (seg == 0 ? lay.cnt0 : (seg == 1 ? lay.cnt1 : (seg == 2 ? lay.cnt2 : lay.cnt3)))) {
                 const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
                 r = load_ray(in, j, c);
-                const HitRec hr = in.h[j];
+                const HitRec hr = stream_load(in.h + j);
                 skip_leaf = hr.leaf;
-                const float4 th4 = in.t[j];
+                const float4 th4 = stream_load(in.t + j);
                 thr = mk3(th4.x, th4.y, th4.z);
                 alive = scatter<MEDIA, RICH>(scatter_mat(seg), a, prims, frames, perlins, s_lights, r, hr, c, thr);
                 ends = !alive; // depth limit: zero radiance
@@ -327,14 +339,14 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BL
         const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
         if (dest >= 0) { // ray + path state + hit go to the queue of the material the ray landed on
             const RayQueue &out = a.pool.mat[parity ^ 1][dest];
-            out.a[e] = make_double2(r.ox, r.oy);
+            stream_store(out.a + e, make_double2(r.ox, r.oy));
             RayB b;
             b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
-            out.b[e] = b;
+            stream_store(out.b + e, b);
             c.dz = r.dz, c.time = r.time;
-            out.c[e] = c;
-            out.t[e] = make_float4(thr.x, thr.y, thr.z, 0.0f);
-            out.h[e] = h;
+            stream_store(out.c + e, c);
+            stream_store(out.t + e, make_float4(thr.x, thr.y, thr.z, 0.0f));
+            stream_store(out.h + e, h);
         }
     }
     // closest-hit queries of this wave -> the render's ray count
@@ -467,8 +479,8 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
                     if (j < (seg == 0 ? lay.cnt0 : (seg == 1 ? lay.cnt1 : (seg == 2 ? lay.cnt2 : lay.cnt3)))) {
                         const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
                         nr = load_ray(in, j, nc);
-                        const HitRec hr = in.h[j];
-                        const float4 th4 = in.t[j];
+                        const HitRec hr = stream_load(in.h + j);
+                        const float4 th4 = stream_load(in.t + j);
                         nthr = mk3(th4.x, th4.y, th4.z);
                         alive = scatter<MEDIA, true>(scatter_mat(seg), a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
                         if (!alive && !finite3(nthr)) splat(a, nc.pixel, nthr, mk3(0.0f, 0.0f, 0.0f)); // depth limit: a NaN throughput still reaches the pixel
@@ -553,14 +565,14 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
             const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
             if (dest >= 0) {
                 const RayQueue &out = a.pool.mat[parity ^ 1][dest];
-                out.a[e] = make_double2(r.ox, r.oy);
+                stream_store(out.a + e, make_double2(r.ox, r.oy));
                 RayB b;
                 b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
-                out.b[e] = b;
+                stream_store(out.b + e, b);
                 c.dz = r.dz, c.time = r.time;
-                out.c[e] = c;
-                out.t[e] = make_float4(thr.x, thr.y, thr.z, 0.0f);
-                out.h[e] = h;
+                stream_store(out.c + e, c);
+                stream_store(out.t + e, make_float4(thr.x, thr.y, thr.z, 0.0f));
+                stream_store(out.h + e, h);
             }
         }
     }

@@ -1,6 +1,6 @@
 """Throughput of the BASELINE.json configurations other than the headline (parity-test cases, not bench lines).
 
-    python tools/scene_perf.py [scene[:spp] ...]      # prints one JSON line per scene
+    python tools/scene_perf.py [scene[:spp[:width]] ...]      # prints one JSON line per scene
 """
 import importlib
 import json
@@ -19,18 +19,19 @@ def main():
     api = rt.api
     ctx = api.Context(0)
     for spec in (sys.argv[1:] or DEFAULT):
-        name, _, spp = spec.partition(":")
-        spp = int(spp or 16)
+        name, _, rest = spec.partition(":")
+        spp, _, width = rest.partition(":")
+        spp, width = int(spp or 16), (int(width) if width else None)
         t0 = time.perf_counter()
         hs = api.HostScene(name, seed=1)
         t1 = time.perf_counter()
         scene = api.Scene(ctx, hs.desc)
         info = scene.info()
         cam = hs.camera()
-        p = hs.params(spp=spp)
-        scene.render(cam, hs.params(spp=1))  # warm-up (allocations, module load)
+        p = hs.params(spp=spp, width=width)
+        scene.render(cam, hs.params(spp=1, width=width))  # warm-up (allocations, module load)
         img, _, st = scene.render(cam, p)
-        pp = hs.params(spp=spp, flags=api.FLAG_PROFILE)
+        pp = hs.params(spp=spp, width=width, flags=api.FLAG_PROFILE)
         _, _, sp = scene.render(cam, pp)
         print(json.dumps({
             "scene": name, "image": [p.width, p.height], "spp": spp, "prims": info.n_prims, "bvh_nodes": info.n_bvh_nodes,

@@ -429,6 +429,9 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     rp.n_pixels = uint32_t(p.width) * uint32_t(p.height);
     rp.total_paths = p.max_depth == 0 ? 0ull : (unsigned long long)rp.n_pixels * (unsigned long long)rp.n_samples; // depth 0: ray_color returns black at once
     rp.pool = int32_t(want_pool);
+    rp.tile_shift = 16; // 65536 pixels = 768 KB of sums per tile; fewer when the sample count is huge (tile_paths <= 2^30)
+    while (rp.tile_shift > 5 && (uint64_t(rp.n_samples) << rp.tile_shift) > (1ull << 30)) --rp.tile_shift;
+    rp.tile_paths = uint32_t(rp.n_samples) << rp.tile_shift;
     DCamera &c = args.cam;
     for (int k = 0; k < 3; ++k) {
         c.origin[k] = camera->origin[k];

@@ -133,6 +133,8 @@ struct DRenderParams {
     unsigned long long total_paths;
     uint32_t n_pixels;
     int32_t pool;
+    uint32_t tile_shift; // paths start tile by tile of 2^tile_shift pixels (render.cu: generate_ray)
+    uint32_t tile_paths; // n_samples << tile_shift, at most 2^30
 };
 
 // Philox counter "stream" words (counter[2]); counter = {sample, bounce, stream, block}.

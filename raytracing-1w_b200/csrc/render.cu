@@ -124,11 +124,21 @@ RT1W_DEV uint32_t purpose_word(const DRenderParams &rp, uint32_t stream) { retur
 // ------------------------------------------------------------------------------------------
 // a new camera path (main.rs:968-971, camera.rs:61-73, math.rs:30-37)
 // ------------------------------------------------------------------------------------------
-// Path number path0 + i of the render = (sample s0 + (p0 + i) / n_pixels, pixel seed (p0 + i) % n_pixels) with
-// s0 = path0 / n_pixels, p0 = path0 % n_pixels split once per CTA (64-bit) instead of once per path.
-RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t s0, uint32_t p0, uint32_t i, uint32_t &state, uint32_t &seed_out) {
-    const uint32_t q = p0 + i, ds = q / a.rp.n_pixels;
-    const uint32_t seed = q - ds * a.rp.n_pixels, sample_rel = s0 + ds;
+// Path numbering.  Paths are started tile by tile: all samples of a tile of 2^tile_shift consecutive pixels (sample
+// by sample, pixel by pixel inside it) before the next tile, so that the pixels the paths in flight add to - a wave
+// holds millions of paths - stay a small, L2-resident part of a big image (3840x2160: 100 MB of sums).  A small
+// image is one tile, i.e. sample-major order.  Path number path0 + i = tile t0 + (w0 + i) / tile_paths, position
+// (w0 + i) % tile_paths inside it, with t0 = path0 / tile_paths and w0 = path0 % tile_paths split once per CTA.
+RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t t0, uint32_t w0, uint32_t i, uint32_t &state, uint32_t &seed_out) {
+    const uint32_t w = w0 + i, dt = w / a.rp.tile_paths;
+    const uint32_t within = w - dt * a.rp.tile_paths, first = (t0 + dt) << a.rp.tile_shift;
+    uint32_t sample_rel, seed;
+    if (a.rp.n_pixels - first >= (1u << a.rp.tile_shift)) { // a whole tile
+        sample_rel = within >> a.rp.tile_shift, seed = first + (within & ((1u << a.rp.tile_shift) - 1u));
+    } else { // the last, partial tile
+        const uint32_t tp = a.rp.n_pixels - first;
+        sample_rel = within / tp, seed = first + (within - sample_rel * tp);
+    }
     const uint32_t j = seed / uint32_t(a.rp.width), col = seed - j * uint32_t(a.rp.width);
     Rng rng;
     rng.k0 = seed, rng.k1 = a.rp.seed_lo;
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BL
     __shared__ unsigned int s_traced;
     // the wave's layout, read back from shared memory inside the loop instead of pinning a dozen registers
     struct Layout {
-        uint32_t off1, off2, off3, off4, cnt0, cnt1, cnt2, cnt3, total, gen_s0, gen_p0;
+        uint32_t off1, off2, off3, off4, cnt0, cnt1, cnt2, cnt3, total, gen_t0, gen_w0;
     };
     __shared__ Layout s_layout;
     uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
@@ -257,8 +267,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BL
         s_traced = 0;
         Layout l;
         l.off1 = off1, l.off2 = off2, l.off3 = off3, l.off4 = off4, l.cnt0 = cnt0, l.cnt1 = cnt1, l.cnt2 = cnt2, l.cnt3 = cnt3, l.total = total;
-        // path number path0 + i = (sample gen_s0 + (gen_p0 + i) / n_pixels, pixel (gen_p0 + i) % n_pixels): one 64-bit division per CTA
-        l.gen_s0 = uint32_t(path0 / a.rp.n_pixels), l.gen_p0 = uint32_t(path0 - (unsigned long long)l.gen_s0 * a.rp.n_pixels);
+        l.gen_t0 = uint32_t(path0 / a.rp.tile_paths), l.gen_w0 = uint32_t(path0 - (unsigned long long)l.gen_t0 * a.rp.tile_paths); // see generate_ray
         s_layout = l;
     }
     if (FLAT) flat_stage(a.sc, s_flat[0]);
@@ -300,7 +309,7 @@ __global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BL
                 ends = !alive; // depth limit: zero radiance
             }
         } else if (i < lay.total) { // a new camera path
-            r = generate_ray(a, lay.gen_s0, lay.gen_p0, i - off4, c.state, c.pixel);
+            r = generate_ray(a, lay.gen_t0, lay.gen_w0, i - off4, c.state, c.pixel);
             thr = mk3(1.0f, 1.0f, 1.0f);
             alive = true;
         }
@@ -379,7 +388,7 @@ constexpr int kPersistentFromNodes = 32768;
 constexpr int kRing = 64; // rays per warp ring; a block is produced whenever 32 entries are free
 
 struct WaveLayout { // thread index space of a wave: [lambertian hits | metal | dielectric | isotropic | new paths]
-    uint32_t off1, off2, off3, off4, cnt0, cnt1, cnt2, cnt3, total, gen_s0, gen_p0;
+    uint32_t off1, off2, off3, off4, cnt0, cnt1, cnt2, cnt3, total, gen_t0, gen_w0;
 };
 
 struct __align__(16) RingRay { // 64 bytes: a ray and the state of its path, between scatter and traversal
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
             s_traced = 0, s_next = 0;
             WaveLayout l;
             l.off1 = off1, l.off2 = off2, l.off3 = off3, l.off4 = off4, l.cnt0 = cnt0, l.cnt1 = cnt1, l.cnt2 = cnt2, l.cnt3 = cnt3, l.total = total;
-            l.gen_s0 = uint32_t(path0 / a.rp.n_pixels), l.gen_p0 = uint32_t(path0 - (unsigned long long)l.gen_s0 * a.rp.n_pixels);
+            l.gen_t0 = uint32_t(path0 / a.rp.tile_paths), l.gen_w0 = uint32_t(path0 - (unsigned long long)l.gen_t0 * a.rp.tile_paths); // see generate_ray
             s_layout = l;
         }
     }
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
                         if (!alive && !finite3(nthr)) splat(a, nc.pixel, nthr, mk3(0.0f, 0.0f, 0.0f)); // depth limit: a NaN throughput still reaches the pixel
                     }
                 } else if (i < lay.total) { // a new camera path
-                    nr = generate_ray(a, lay.gen_s0, lay.gen_p0, i - off4, nc.state, nc.pixel);
+                    nr = generate_ray(a, lay.gen_t0, lay.gen_w0, i - off4, nc.state, nc.pixel);
                     nthr = mk3(1.0f, 1.0f, 1.0f);
                     alive = true;
                 }

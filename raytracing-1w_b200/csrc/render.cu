@@ -36,7 +36,10 @@ namespace rt1w {
 #define RT1W_FLAT_MIN_BLOCKS 5 // CTAs per SM of the flat-scan wave kernel with media; one more (80 registers, no spills) without
 #endif
 #ifndef RT1W_BVH_MIN_BLOCKS
-#define RT1W_BVH_MIN_BLOCKS 4
+#define RT1W_BVH_MIN_BLOCKS 5 // lockstep BVH wave kernel with media; one more without
+#endif
+#ifndef RT1W_PERSISTENT_MIN_BLOCKS
+#define RT1W_PERSISTENT_MIN_BLOCKS 4 // persistent BVH wave kernel: more resident rays only thrash L1 on the big trees it is used for
 #endif
 #ifndef RT1W_GRID_PER_SM
 #define RT1W_GRID_PER_SM 8
@@ -225,7 +228,7 @@ template <bool FLAT, bool MEDIA, bool RICH>
 #ifdef RT1W_REGS_FROM_FLAG // sweeps: register budget from --maxrregcount instead of the launch bounds
 __global__ void
 #else
-__global__ void __launch_bounds__(kWaveThreads, FLAT ? (MEDIA ? RT1W_FLAT_MIN_BLOCKS : RT1W_FLAT_MIN_BLOCKS + 1) : RT1W_BVH_MIN_BLOCKS)
+__global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) + (MEDIA ? 0 : 1))
 #endif
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
@@ -401,7 +404,7 @@ struct __align__(16) RingRay { // 64 bytes: a ray and the state of its path, bet
 static_assert(sizeof(RingRay) == 64, "RingRay must be 4 x 16 bytes");
 
 template <bool MEDIA>
-__global__ void __launch_bounds__(kWaveThreads, RT1W_BVH_MIN_BLOCKS)
+__global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     k_wave_bvh(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
     __shared__ uint2 s_stack[kStackSmem * kWaveThreads];

@@ -696,7 +696,8 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     const WaveKernel kernel = flat ? (media ? (rich ? k_wave<true, true, true> : k_wave<true, true, false>)
                                             : (rich ? k_wave<true, false, true> : k_wave<true, false, false>))
                               : persistent ? (media ? k_wave_bvh<true> : k_wave_bvh<false>)
-                                           : (media ? k_wave<false, true, true> : k_wave<false, false, true>);
+                                           : (media ? (rich ? k_wave<false, true, true> : k_wave<false, true, false>)
+                                                    : (rich ? k_wave<false, false, true> : k_wave<false, false, false>));
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWaveThreads, perlin_bytes)) != cudaSuccess) return e;

@@ -23,11 +23,6 @@
 namespace rt1w {
 
 #define RT1W_DEV __device__ __forceinline__
-#ifdef RT1W_OUTLINE_SHADE // experiment: one copy of the big shading helpers instead of one per material
-#define RT1W_DEV_BIG static __device__ __noinline__
-#else
-#define RT1W_DEV_BIG __device__ __forceinline__
-#endif
 
 constexpr double kTMin = 0.001;      // main.rs:62
 constexpr float kPiF = 3.14159265358979323846f;
@@ -649,7 +644,7 @@ RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
 
 // P: the primitive's record, frames: the wrapper frames (global memory or the flat scan's shared-memory copies).
 // `side`: which rectangle of a P_BOX was hit (see kLeafBits).
-template <bool WANT_UV> RT1W_DEV_BIG HitInfo finalize_hit(const DPrim *P, const DFrame *frames, int side, const Ray &r, double t) {
+template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const DPrim *P, const DFrame *frames, int side, const Ray &r, double t) {
     HitInfo h;
     const double2 *w = reinterpret_cast<const double2 *>(P);
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3);

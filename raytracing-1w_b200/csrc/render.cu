@@ -41,9 +41,6 @@ namespace rt1w {
 #ifndef RT1W_PERSISTENT_MIN_BLOCKS
 #define RT1W_PERSISTENT_MIN_BLOCKS 4 // persistent BVH wave kernel: more resident rays only thrash L1 on the big trees it is used for
 #endif
-#ifndef RT1W_GRID_PER_SM
-#define RT1W_GRID_PER_SM 8
-#endif
 constexpr int kWaveThreads = RT1W_WAVE_THREADS;
 constexpr int kExtendThreads = kWaveThreads; // k_trace shares the traversal-stack geometry
 
@@ -225,11 +222,7 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 // RICH: some texture is not a SolidColor (else checker / Perlin / image code is compiled out: a third of the kernel).
 template <bool FLAT, bool MEDIA, bool RICH>
-#ifdef RT1W_REGS_FROM_FLAG // sweeps: register budget from --maxrregcount instead of the launch bounds
-__global__ void
-#else
 __global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) + (MEDIA ? 0 : 1))
-#endif
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
     // one static buffer: the staged primitive list + entry-distance table (FLAT) or the per-thread traversal stacks (BVH)

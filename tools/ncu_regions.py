@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def function_starts(path):
     starts = []
     for n, line in enumerate(open(path), 1):
-        m = re.match(r"(?:template <[^>]*>\s*)?(?:RT1W_DEV_BIG|RT1W_DEV|__global__|static|RT1W_HD)\s.*?(\w+)\(", line)
+        m = re.match(r"(?:template <[^>]*>\s*)?(?:RT1W_DEV|__global__|static|RT1W_HD)\s.*?(\w+)\(", line)
         if m and not line.startswith(" "):
             starts.append((n, m.group(1)))
     return starts

@@ -1,9 +1,11 @@
 // api.cu — the C ABI of include/rt1w.h: handles, scene commit (lowering + SAH build + upload),
 // render entry points, the closest-hit parity hook and the host-side output quantisation.
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -67,6 +69,61 @@ void local_bounds(const rt1w_flat_prim &fp, double lo[3], double hi[3]) {
     default: // not expected (moving spheres keep their world box)
         for (int c = 0; c < 3; ++c) lo[c] = fp.bbox_min[c], hi[c] = fp.bbox_max[c];
         break;
+    }
+}
+
+// Face groups of the flat scan.  A rectangle is a face of the box B when its plane is one of B's bounds on its axis and
+// its in-plane intervals are exactly B's on the two other axes.  Two rectangles of different axes in one frame fix a
+// box; every unassigned rectangle of the frame that is a face of it joins, one per face.  Groups of fewer than three
+// faces are not worth the shared slab computation.  `order`: leaf -> index into dev.  Output per leaf: group number
+// and face = 2 * axis + (upper plane ? 1 : 0), or -1; per group: the box (min xyz, max xyz).
+void find_face_groups(const std::vector<rt1w_flat_prim> &dev, const std::vector<uint32_t> &order, std::vector<int> &face_group,
+                      std::vector<int> &face_of, std::vector<std::array<double, 6>> &group_box) {
+    const int n = int(order.size());
+    auto prim = [&](int leaf) -> const rt1w_flat_prim & { return dev[order[leaf]]; };
+    auto axis_of = [&](int leaf) {
+        const int kind = prim(leaf).kind;
+        return kind == RT1W_NODE_YZ_RECT ? 0 : (kind == RT1W_NODE_XZ_RECT ? 1 : (kind == RT1W_NODE_XY_RECT ? 2 : -1));
+    };
+    // extents of a rectangle: lo / hi on its two in-plane axes, plane on its own
+    auto rect_extents = [&](int leaf, double lo[3], double hi[3]) {
+        const int ax = axis_of(leaf), a = ax == 0 ? 1 : 0, b = ax == 2 ? 1 : 2;
+        const double *p = prim(leaf).p;
+        lo[a] = p[0], hi[a] = p[1], lo[b] = p[2], hi[b] = p[3], lo[ax] = hi[ax] = p[4];
+    };
+    auto face_in = [&](int leaf, const std::array<double, 6> &box) { // face number of the rectangle in the box, or -1
+        const int ax = axis_of(leaf);
+        double lo[3], hi[3];
+        rect_extents(leaf, lo, hi);
+        for (int c = 0; c < 3; ++c)
+            if (c != ax && (lo[c] != box[c] || hi[c] != box[3 + c])) return -1;
+        if (lo[ax] == box[ax]) return 2 * ax;
+        if (lo[ax] == box[3 + ax]) return 2 * ax + 1;
+        return -1;
+    };
+    for (int r1 = 0; r1 < n; ++r1) {
+        if (axis_of(r1) < 0 || face_group[r1] >= 0) continue;
+        for (int r2 = 0; r2 < n; ++r2) {
+            if (r2 == r1 || axis_of(r2) < 0 || axis_of(r2) == axis_of(r1) || face_group[r2] >= 0 || prim(r2).frame != prim(r1).frame) continue;
+            std::array<double, 6> box;
+            double lo[3], hi[3], lo2[3], hi2[3];
+            rect_extents(r1, lo, hi), rect_extents(r2, lo2, hi2);
+            const int ax = axis_of(r1);
+            for (int c = 0; c < 3; ++c) box[c] = c == ax ? lo2[c] : lo[c], box[3 + c] = c == ax ? hi2[c] : hi[c];
+            if (!(box[0] < box[3] && box[1] < box[4] && box[2] < box[5])) continue;
+            if (face_in(r1, box) < 0 || face_in(r2, box) < 0) continue;
+            int members[6] = {-1, -1, -1, -1, -1, -1}, count = 0;
+            for (int r = 0; r < n; ++r) {
+                if (axis_of(r) < 0 || face_group[r] >= 0 || prim(r).frame != prim(r1).frame) continue;
+                const int f = face_in(r, box);
+                if (f >= 0 && members[f] < 0) members[f] = r, ++count;
+            }
+            if (count < 3) continue;
+            for (int f = 0; f < 6; ++f)
+                if (members[f] >= 0) face_group[members[f]] = int(group_box.size()), face_of[members[f]] = f;
+            group_box.push_back(box);
+            break;
+        }
     }
 }
 
@@ -282,6 +339,12 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
             }
         }
         const double scan_pad = 1e-6 * reach;
+        // Face groups (kernels.cuh: closest_hit_flat): rectangles of one frame that are whole faces of a common box -
+        // the walls of a room, the sides of an AABox (aabox.rs:29-76) - are tested with ONE slab computation on that box.
+        std::vector<int> face_group(n, -1), face_of(n, -1); // by leaf
+        std::vector<std::array<double, 6>> group_box;
+        const char *fg_env = std::getenv("RT1W_FACE_GROUPS"); // =0: one box per rectangle (A/B measurements, tests)
+        if (!fg_env || std::strcmp(fg_env, "0") != 0) find_face_groups(dev, bvh.prim_order, face_group, face_of, group_box);
         std::vector<int> scan(n);
         for (size_t i = 0; i < n; ++i) scan[i] = int(i);
         auto box_frame = [&](int leaf) { // a moving sphere keeps its world box: the reference tests that box (bvh.rs:31) before
@@ -293,24 +356,45 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
             const rt1w_flat_prim &fp = dev[bvh.prim_order[leaf]];
             return fp.kind == RT1W_NODE_SPHERE ? 1 : 0;
         };
+        auto scan_class = [&](int leaf) { return face_group[leaf] >= 0 ? 0 : 1 + is_sphere(leaf); }; // face groups, other boxes, plain spheres
         std::stable_sort(scan.begin(), scan.end(), [&](int a, int b) {
-            return box_frame(a) != box_frame(b) ? box_frame(a) < box_frame(b) : is_sphere(a) < is_sphere(b);
+            if (box_frame(a) != box_frame(b)) return box_frame(a) < box_frame(b);
+            if (scan_class(a) != scan_class(b)) return scan_class(a) < scan_class(b);
+            if (face_group[a] != face_group[b]) return face_group[a] < face_group[b];
+            return face_of[a] < face_of[b];
         });
-        for (size_t k = 0; k < n; ++k) {
+        for (size_t k = 0; k < n; ++k) { // three float4 per scan slot: (lo.xyz, leaf), (hi.xyz, frame), (face group + 1, face, delta, -)
             const rt1w_flat_prim &fp = dev[bvh.prim_order[scan[k]]];
             const int bf = box_frame(scan[k]);
             double dlo[3], dhi[3];
-            if (bf < 0) {
-                for (int c = 0; c < 3; ++c) dlo[c] = fp.bbox_min[c], dhi[c] = fp.bbox_max[c];
-            } else {
-                local_bounds(fp, dlo, dhi);
-            }
             float lo[3], hi[3];
-            conservative_box(dlo, dhi, lo, hi, scan_pad);
+            float4 extra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const int fg = face_group[scan[k]];
+            if (fg >= 0) { // every face slot carries the group's box, its planes moved outward by the f32 error of a tagged plane
+                           // distance: 2^-23 |o| + (2^-22 + 2^-21) |plane - o| in space units, below 2e-6 reach for origins
+                           // within 2 x reach (see scan_pad).  A rectangle is hit ON its plane: its +-0.0001 slab is not needed.
+                const double face_pad = 3e-6 * reach;
+                double pad = 0.0; // distance of the padded planes from the true faces after rounding outward
+                for (int c = 0; c < 3; ++c) {
+                    lo[c] = std::nextafter(float(group_box[fg][c] - face_pad), -std::numeric_limits<float>::infinity());
+                    hi[c] = std::nextafter(float(group_box[fg][3 + c] + face_pad), std::numeric_limits<float>::infinity());
+                    pad = std::max(pad, std::max(group_box[fg][c] - double(lo[c]), double(hi[c]) - group_box[fg][3 + c]));
+                }
+                const int32_t g1 = fg + 1, face = face_of[scan[k]];
+                std::memcpy(&extra.x, &g1, 4), std::memcpy(&extra.y, &face, 4);
+                extra.z = float(2.02 * pad);
+            } else {
+                if (bf < 0) {
+                    for (int c = 0; c < 3; ++c) dlo[c] = fp.bbox_min[c], dhi[c] = fp.bbox_max[c];
+                } else {
+                    local_bounds(fp, dlo, dhi);
+                }
+                conservative_box(dlo, dhi, lo, hi, scan_pad);
+            }
             float4 l = make_float4(lo[0], lo[1], lo[2], 0.0f), h = make_float4(hi[0], hi[1], hi[2], 0.0f);
             const int32_t leaf = scan[k], frame = bf;
             std::memcpy(&l.w, &leaf, 4), std::memcpy(&h.w, &frame, 4);
-            prim_boxes.push_back(l), prim_boxes.push_back(h);
+            prim_boxes.push_back(l), prim_boxes.push_back(h), prim_boxes.push_back(extra);
         }
     }
     const auto t1 = std::chrono::steady_clock::now();
@@ -432,6 +516,8 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     rp.tile_shift = 16; // 65536 pixels = 768 KB of sums per tile; fewer when the sample count is huge (tile_paths <= 2^30)
     while (rp.tile_shift > 5 && (uint64_t(rp.n_samples) << rp.tile_shift) > (1ull << 30)) --rp.tile_shift;
     rp.tile_paths = uint32_t(rp.n_samples) << rp.tile_shift;
+    rp.inv_w1 = 1.0 / double(p.width - 1), rp.inv_h1 = 1.0 / double(p.height - 1); // a 1-pixel axis: inf, as the reference's division by zero
+    rp.inv_width_up = (1.0 / double(p.width)) * (1.0 + 0x1p-50), rp.inv_tile_paths_up = (1.0 / double(rp.tile_paths)) * (1.0 + 0x1p-50);
     DCamera &c = args.cam;
     for (int k = 0; k < 3; ++k) {
         c.origin[k] = camera->origin[k];

@@ -135,6 +135,9 @@ struct DRenderParams {
     int32_t pool;
     uint32_t tile_shift; // paths start tile by tile of 2^tile_shift pixels (render.cu: generate_ray)
     uint32_t tile_paths; // n_samples << tile_shift, at most 2^30
+    // reciprocals prepared by the host: 1 / (width - 1), 1 / (height - 1) (main.rs:968-969) and, rounded UP so that
+    // uint32(double(n) * r) == n / d for every n < 2^32 with n / d * d < 2^50, 1 / width and 1 / tile_paths
+    double inv_w1, inv_h1, inv_width_up, inv_tile_paths_up;
 };
 
 // Philox counter "stream" words (counter[2]); counter = {sample, bounce, stream, block}.

@@ -446,11 +446,16 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
 //     divergence).  Boxes are the primitives' bounds in their OWN frame (tight around rotated box sides),
 //     grouped by frame so the ray is re-expressed once per group; the entry distance of every box the ray
 //     crosses beyond t_min is parked in shared memory and the nearest one is tracked.
+//     Rectangles that are whole faces of one axis-aligned box in a frame (the five walls of the Cornell room, the
+//     six sides of an AABox, aabox.rs:29-76) form a FACE GROUP (api.cu: find_face_groups): ONE slab computation on
+//     the box names the face the ray enters through and the one it leaves through (the plane distances carry
+//     their face number in the three lowest mantissa bits through the min / max network), and only those two
+//     become candidates.  Rays that pass an edge of the box within the padding take a per-face path.
 //   pass 2 (per lane, f64): solve the nearest candidate, then the nearest remaining one whose box is entered
 //     before the best hit so far (the entry distance is a lower bound of the primitive's t), and so on:
 //     ~1.2 solves per ray.
 #ifndef RT1W_SCAN_UNROLL
-#define RT1W_SCAN_UNROLL 4
+#define RT1W_SCAN_UNROLL 1 // the wave kernel is bound by its instruction-cache footprint: unrolling by 4 was 5 % slower
 #endif
 constexpr int kScanUnroll = RT1W_SCAN_UNROLL;
 #ifdef RT1W_COUNT_SOLVES // measurement build (build.py --variant count -DRT1W_COUNT_SOLVES): rays, pass-1 candidates, f64 solves, warp-level solve iterations
@@ -458,17 +463,22 @@ static __device__ unsigned long long g_scan_counts[4];
 #endif
 constexpr int kFlatMax = 32;
 constexpr int kFlatMaxFrames = 8;
+enum FlatGroupKind : int { G_BOXES = 0, G_SPHERES = 1, G_FACES = 2 };
 
 struct FlatScene {
     DPrim prims[kFlatMax];             // leaf order
     float4 lo[kFlatMax], hi[kFlatMax]; // scan order: padded f32 bounds in the frame of the group; lo.w = leaf (int bits)
     float4 sphere[kFlatMax];           // scan order, sphere groups: centre and radius in f32
     DFrame frames[kFlatMaxFrames];
-    // scan-order groups: group g = boxes [group_end[g-1], group_end[g]) in frame group_frame[g] (-1 = world);
-    // group_sphere[g]: plain spheres, screened by an f32 discriminant on top of the box
-    int32_t group_end[2 * kFlatMaxFrames + 2];
-    int32_t group_frame[2 * kFlatMaxFrames + 2];
-    int32_t group_sphere[2 * kFlatMaxFrames + 2];
+    // scan-order groups: group g = boxes [group_end[g-1], group_end[g]) in frame group_frame[g] (-1 = world).
+    // group_kind[g]: G_BOXES one box per primitive; G_SPHERES plain spheres, screened by an f32 discriminant on top of
+    // the box; G_FACES rectangles that are faces of ONE box (every slot of the group carries that box): face_slot[g][f]
+    // = scan slot of face f (2 * axis + (upper plane ? 1 : 0)) or -1, group_delta[g] = twice the box padding
+    int32_t group_end[kFlatMax];
+    int32_t group_frame[kFlatMax];
+    int32_t group_kind[kFlatMax];
+    float group_delta[kFlatMax];
+    int8_t face_slot[kFlatMax][8];
     int32_t n_groups;
     uint32_t skip_bit[kFlatMax]; // leaf -> scan bit of a rectangle (a ray leaving a rectangle cannot hit it again), else 0
 };
@@ -484,19 +494,27 @@ RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the 
     src = reinterpret_cast<const uint32_t *>(sc.frames), dst = reinterpret_cast<uint32_t *>(fs.frames);
     for (int w = threadIdx.x; w < sc.n_frames * int(sizeof(DFrame) / 4); w += blockDim.x) dst[w] = src[w];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float4 lo = sc.prim_boxes[2 * i], hi = sc.prim_boxes[2 * i + 1];
+        const float4 lo = sc.prim_boxes[3 * i], hi = sc.prim_boxes[3 * i + 1];
         fs.lo[i] = lo, fs.hi[i] = hi;
         const DPrim &p = sc.prims[__float_as_int(lo.w)];
         fs.sphere[i] = make_float4(float(p.p[0]), float(p.p[1]), float(p.p[2]), float(p.p[3]));
         const int type = int(p.meta & 15u);
         fs.skip_bit[__float_as_int(lo.w)] = (type == P_XY_RECT || type == P_XZ_RECT || type == P_YZ_RECT) ? 1u << i : 0u;
     }
-    if (threadIdx.x == 0) { // the host lists the boxes frame by frame, plain spheres last within a frame (hi.w = frame of the box)
-        int g = 0;
+    if (threadIdx.x == 0) { // the host lists the boxes frame by frame: face groups, other boxes, plain spheres (hi.w = frame of the box)
+        int g = 0, prev_group = -1;
         for (int i = 0; i < n; ++i) {
-            const int frame = __float_as_int(sc.prim_boxes[2 * i + 1].w);
-            const int sph = flat_is_sphere(sc.prims[__float_as_int(sc.prim_boxes[2 * i].w)], frame) ? 1 : 0;
-            if (i == 0 || frame != fs.group_frame[g - 1] || sph != fs.group_sphere[g - 1]) fs.group_frame[g] = frame, fs.group_sphere[g] = sph, ++g;
+            const int frame = __float_as_int(sc.prim_boxes[3 * i + 1].w);
+            const float4 extra = sc.prim_boxes[3 * i + 2]; // face groups: x = group number + 1 (0: none), y = face, z = delta
+            const int face_group = __float_as_int(extra.x) - 1;
+            const int kind = face_group >= 0 ? int(G_FACES) : (flat_is_sphere(sc.prims[__float_as_int(sc.prim_boxes[3 * i].w)], frame) ? int(G_SPHERES) : int(G_BOXES));
+            if (i == 0 || frame != fs.group_frame[g - 1] || kind != fs.group_kind[g - 1] || face_group != prev_group) {
+                fs.group_frame[g] = frame, fs.group_kind[g] = kind, fs.group_delta[g] = extra.z;
+                for (int f = 0; f < 8; ++f) fs.face_slot[g][f] = int8_t(-1);
+                ++g;
+            }
+            prev_group = face_group;
+            if (kind == int(G_FACES)) fs.face_slot[g - 1][__float_as_int(extra.y) & 7] = int8_t(i);
             fs.group_end[g - 1] = i + 1;
         }
         fs.n_groups = g;
@@ -525,6 +543,9 @@ RT1W_DEV bool slab_fma(const float4 lo, const float4 hi, const SlabRayF &s, floa
     const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
     return tnear <= tf;
 }
+
+// a plane distance with its face number in the three lowest mantissa bits (face groups)
+RT1W_DEV float face_tag(float t, uint32_t face) { return __uint_as_float((__float_as_uint(t) & ~7u) | face); }
 
 // f32 screen of a plain sphere on top of its box: false only when the ray certainly misses it beyond t_min
 // (discriminant below its rounding bound, or sphere behind an origin outside it).
@@ -560,7 +581,60 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
                 s = slab_ray(l.ox, l.oy, l.oz, float(l.dx), float(l.dy), float(l.dz));
             }
         }
-        if (fs.group_sphere[g]) {
+        const int kind = fs.group_kind[g];
+        if (kind == int(G_FACES)) {
+            // One slab computation for all faces of the group's box.  Plane distances are tagged with their face number
+            // (lowest three mantissa bits), so the entry distance max(near) and the exit distance min(far) name their face.
+            const float4 lo = fs.lo[k], hi = fs.hi[k];
+            const float ax = face_tag(fmaf(lo.x, s.ix, s.ox), 0u), bx = face_tag(fmaf(hi.x, s.ix, s.ox), 1u);
+            const float ay = face_tag(fmaf(lo.y, s.iy, s.oy), 2u), by = face_tag(fmaf(hi.y, s.iy, s.oy), 3u);
+            const float az = face_tag(fmaf(lo.z, s.iz, s.oz), 4u), bz = face_tag(fmaf(hi.z, s.iz, s.oz), 5u);
+            const float nx = fminf(ax, bx), ny = fminf(ay, by), nz = fminf(az, bz);
+            const float fx = fmaxf(ax, bx), fy = fmaxf(ay, by), fz = fmaxf(az, bz);
+            const float tn_raw = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);
+            const float tn = fmaxf(tn_raw, kTMinSlab);
+            if (tn <= tf) {
+                // A computed plane distance is within 2 * padding / |d_axis| of the true one (the padding covers the
+                // rounding, see slab_fma): with delta = the sum over the axes, the face named by max / min is the true one
+                // whenever the runner-up is further than delta away.
+                const float delta = fs.group_delta[g] * (fabsf(s.ix) + fabsf(s.iy) + fabsf(s.iz));
+                const float mid_n = fmaxf(fminf(nx, ny), fminf(fmaxf(nx, ny), nz));
+                const float mid_f = fminf(fmaxf(fx, fy), fmaxf(fminf(fx, fy), fz));
+                // the padded planes are crossed before the true ones: an entry up to delta before t_min may be a hit beyond it
+                const bool enters = tn_raw + delta >= kTMinSlab;
+                const int8_t *slots = fs.face_slot[g];
+                if (!((enters && mid_n >= tn_raw - delta) || mid_f <= tf + delta)) { // sure of the entry and of the exit face
+                    if (enters) { // the face the ray enters through (a ray leaving a face of the group names that face: skipped)
+                        const int sl = slots[__float_as_uint(tn_raw) & 7u];
+                        if (sl >= 0 && ((keep >> sl) & 1u)) {
+                            tn_col[sl * stride] = tn, cand |= 1u << sl;
+                            if (tn < t1) t1 = tn, k1 = sl;
+                        }
+                    }
+                    const int sl = slots[__float_as_uint(tf) & 7u]; // the face it leaves through
+                    if (sl >= 0 && ((keep >> sl) & 1u)) {
+                        const float te = fmaxf(tf - delta, tn);
+                        tn_col[sl * stride] = te, cand |= 1u << sl;
+                        if (te < t1) t1 = te, k1 = sl;
+                    }
+                } else { // the ray passes an edge of the box within the padding: every face whose plane it crosses inside the box
+#pragma unroll 1
+                    for (int f = 0; f < 6; ++f) {
+                        const int sl = slots[f];
+                        if (sl < 0 || !((keep >> sl) & 1u)) continue;
+                        const int a = f >> 1;
+                        const float plane = reinterpret_cast<const float *>((f & 1) ? &fs.hi[k] : &fs.lo[k])[a];
+                        const float tp = fmaf(plane, a == 0 ? s.ix : (a == 1 ? s.iy : s.iz), a == 0 ? s.ox : (a == 1 ? s.oy : s.oz));
+                        if (tp + delta >= tn && tp - delta <= tf) {
+                            const float te = fmaxf(tp - delta, tn);
+                            tn_col[sl * stride] = te, cand |= 1u << sl;
+                            if (te < t1) t1 = te, k1 = sl;
+                        }
+                    }
+                }
+            }
+            k = end, bit = uint32_t(1ull << end);
+        } else if (kind == int(G_SPHERES)) {
             f3 o, d; // the ray in the group's frame, f32
             if (frame < 0) {
                 o = mk3(float(r.ox), float(r.oy), float(r.oz)), d = mk3(r.dx, r.dy, r.dz);
@@ -735,6 +809,17 @@ template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const DPrim *P, const DFra
     return h;
 }
 
+// front_face of a hit on a rectangle that sits under no wrapper chain (what finalize_hit computes for it), without the
+// rest of the record: `dot(direction, +axis) < 0` (aarect.rs:62-70 with hittable.rs:30-35), toggled by FlipFace
+// (hittable.rs:290-294).  Returns false for every other primitive.
+RT1W_DEV bool plain_rect_front_face(const DPrim *P, const Ray &r, bool &front_face) {
+    const int type = int(P->meta & 15u);
+    if (P->frame >= 0 || (type != P_XY_RECT && type != P_XZ_RECT && type != P_YZ_RECT)) return false;
+    const float dn = type == P_XY_RECT ? r.dz : (type == P_XZ_RECT ? r.dy : r.dx);
+    front_face = (dn < 0.0f) != (((P->meta >> 4) & PF_FLIP_FACE) != 0u);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Textures (texture.rs, perlin.rs)
 // ------------------------------------------------------------------------------------------
@@ -830,11 +915,12 @@ RT1W_DEV Onb onb_from_w(f3 n) { // onb.rs:13-24
 }
 RT1W_DEV f3 onb_local(const Onb &o, f3 a) { return a.x * o.u + a.y * o.v + a.z * o.w; } // onb.rs:26-28
 
-RT1W_DEV f3 random_in_unit_sphere(Rng &rng) { // math.rs:6-18 (three gen_range(-1..1) per try)
+// math.rs:6-18 (three gen_range(-1..1) per try); `x`: the block the caller already drew, used by the first try
+RT1W_DEV f3 random_in_unit_sphere(Philox4 x, Rng &rng) {
     for (;;) {
-        const Philox4 x = rng.next4();
         const f3 p = mk3(2.0f * u01(x.x) - 1.0f, 2.0f * u01(x.y) - 1.0f, 2.0f * u01(x.z) - 1.0f);
         if (dot(p, p) < 1.0f) return p;
+        x = rng.next4();
     }
 }
 
@@ -897,9 +983,8 @@ RT1W_DEV float reflectance(float cosine, float ref_idx) { // material.rs:121-125
 // A cosine sample (math.rs:39-49) and a sample towards a sphere light (math.rs:51-65, sphere.rs:92-99) are both
 // `onb.local(cos(phi) q, sin(phi) q, z)` with q = sqrt(1 - z^2), about the normal resp. the direction to the
 // sphere, so the two strategies share one code path; a rectangle light (aarect.rs:140-147) is the short branch.
-RT1W_DEV f3 scatter_lambertian(const SceneView &sc, const DLight *lights, const HitInfo &h, Rng &rng, f3 &weight) {
+RT1W_DEV f3 scatter_lambertian(const SceneView &sc, const DLight *lights, const HitInfo &h, const Philox4 x, f3 &weight) {
     const f3 w = normalize(h.normal); // onb.rs:14
-    const Philox4 x = rng.next4();
     const float r1 = u01(x.z), r2 = u01(x.w);
     f3 dir, axis = w;
     float z = sqrtf(1.0f - r2);
@@ -940,18 +1025,18 @@ RT1W_DEV f3 scatter_lambertian(const SceneView &sc, const DLight *lights, const 
     return dir;
 }
 
-RT1W_DEV f3 scatter_metal(const DMaterial &m, const Ray &r, const HitInfo &h, Rng &rng) { // material.rs:98-112
+RT1W_DEV f3 scatter_metal(const DMaterial &m, const Ray &r, const HitInfo &h, const Philox4 x, Rng &rng) { // material.rs:98-112
     const f3 reflected = reflect(normalize(mk3(r.dx, r.dy, r.dz)), h.normal);
-    return reflected + m.fuzz * random_in_unit_sphere(rng);
+    return reflected + m.fuzz * random_in_unit_sphere(x, rng);
 }
 
-RT1W_DEV f3 scatter_dielectric(const DMaterial &m, const Ray &r, const HitInfo &h, Rng &rng) { // material.rs:132-161
+RT1W_DEV f3 scatter_dielectric(const DMaterial &m, const Ray &r, const HitInfo &h, const Philox4 x) { // material.rs:132-161
     const float ratio = h.front_face ? 1.0f / m.ir : m.ir;
     const f3 unit = normalize(mk3(r.dx, r.dy, r.dz));
     const float cos_theta = fminf(dot(-unit, h.normal), 1.0f);
     const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
     bool reflects = ratio * sin_theta > 1.0f;
-    if (!reflects) reflects = reflectance(cos_theta, ratio) > u01(rng.next4().x);
+    if (!reflects) reflects = reflectance(cos_theta, ratio) > u01(x.x);
     return reflects ? reflect(unit, h.normal) : refract(unit, h.normal, ratio);
 }
 

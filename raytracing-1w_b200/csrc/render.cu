@@ -71,9 +71,12 @@ RT1W_DEV uint32_t warp_sort_reserve(uint32_t *n_mat, int dest) {
 // radiance is zero: the reference turns a NaN pixel SUM into black (color.rs:14-21), and
 // `li / pdf` with pdf == 0 is NaN there whatever li is (main.rs:102).
 // `seed`: the path's pixel as the reference numbers it (j * width + i, row j counted from the bottom, main.rs:964).
+// n / d through the host-prepared reciprocal of d rounded up (device_types.h: DRenderParams): three instructions instead of the ~20 of a 32-bit division
+RT1W_DEV uint32_t div_by(uint32_t n, double inv_up) { return __double2uint_rz(double(n) * inv_up); }
+
 RT1W_DEV void splat(const RenderArgs &a, uint32_t seed, f3 thr, f3 radiance) {
     const float c[3] = {thr.x * radiance.x, thr.y * radiance.y, thr.z * radiance.z};
-    const uint32_t j = seed / uint32_t(a.rp.width), col = seed - j * uint32_t(a.rp.width);
+    const uint32_t j = div_by(seed, a.rp.inv_width_up), col = seed - j * uint32_t(a.rp.width);
     const uint32_t pixel = (uint32_t(a.rp.height) - 1u - j) * uint32_t(a.rp.width) + col; // main.rs:959: rows are emitted top first
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -130,7 +133,7 @@ RT1W_DEV uint32_t purpose_word(const DRenderParams &rp, uint32_t stream) { retur
 // image is one tile, i.e. sample-major order.  Path number path0 + i = tile t0 + (w0 + i) / tile_paths, position
 // (w0 + i) % tile_paths inside it, with t0 = path0 / tile_paths and w0 = path0 % tile_paths split once per CTA.
 RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t t0, uint32_t w0, uint32_t i, uint32_t &state, uint32_t &seed_out) {
-    const uint32_t w = w0 + i, dt = w / a.rp.tile_paths;
+    const uint32_t w = w0 + i, dt = div_by(w, a.rp.inv_tile_paths_up);
     const uint32_t within = w - dt * a.rp.tile_paths, first = (t0 + dt) << a.rp.tile_shift;
     uint32_t sample_rel, seed;
     if (a.rp.n_pixels - first >= (1u << a.rp.tile_shift)) { // a whole tile
@@ -139,13 +142,13 @@ RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t t0, uint32_t w0, uint32_
         const uint32_t tp = a.rp.n_pixels - first;
         sample_rel = within / tp, seed = first + (within - sample_rel * tp);
     }
-    const uint32_t j = seed / uint32_t(a.rp.width), col = seed - j * uint32_t(a.rp.width);
+    const uint32_t j = div_by(seed, a.rp.inv_width_up), col = seed - j * uint32_t(a.rp.width);
     Rng rng;
     rng.k0 = seed, rng.k1 = a.rp.seed_lo;
     rng.c0 = uint32_t(a.rp.sample_begin) + sample_rel, rng.c1 = 0, rng.c2 = purpose_word(a.rp, RNG_CAMERA), rng.block = 0;
     const Philox4 x = rng.next4();
-    const double s = (double(col) + double(u01(x.x))) / double(a.rp.width - 1);  // main.rs:968
-    const double t = (double(j) + double(u01(x.y))) / double(a.rp.height - 1);   // main.rs:969
+    const double s = (double(col) + double(u01(x.x))) * a.rp.inv_w1; // main.rs:968
+    const double t = (double(j) + double(u01(x.y))) * a.rp.inv_h1;   // main.rs:969
     double offx = 0.0, offy = 0.0, offz = 0.0;
     if (a.cam.lens_radius != 0.0) { // camera.rs:62-63; the rejection loop of math.rs:30-37
         float px, py;
@@ -190,22 +193,23 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
     Rng rng;
     path_rng_key(a.rp, c.pixel, rng.k0, rng.k1);
     rng.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), rng.c1 = depth, rng.c2 = purpose_word(a.rp, RNG_SCATTER), rng.block = 0;
+    const Philox4 x0 = rng.next4(); // every family starts from this block (one Philox body for the four of them; the Dielectric ignores it on total reflection)
     f3 dir;
     float time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
     if (mat == RT1W_MAT_LAMBERTIAN) {
         const f3 att = texture_value<RICH>(a.sc, perlins, m.texture, h);
         f3 weight;
-        dir = scatter_lambertian(a.sc, lights, h, rng, weight);
+        dir = scatter_lambertian(a.sc, lights, h, x0, weight);
         thr = thr * att * weight;
         time = float(hr.t); // main.rs:86,145: the scattered ray's time is the hit parameter t
     } else if (mat == RT1W_MAT_METAL) {
-        dir = scatter_metal(m, r, h, rng);
+        dir = scatter_metal(m, r, h, x0, rng);
         thr = thr * mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
     } else if (mat == RT1W_MAT_DIELECTRIC || !MEDIA) {
-        dir = scatter_dielectric(m, r, h, rng); // attenuation (1,1,1)
+        dir = scatter_dielectric(m, r, h, x0); // attenuation (1,1,1)
     } else {                                    // Isotropic, constant_medium.rs:36-51
         thr = thr * texture_value<RICH>(a.sc, perlins, m.texture, h);
-        dir = random_in_unit_sphere(rng);
+        dir = random_in_unit_sphere(x0, rng);
     }
     if (depth + 1u >= uint32_t(a.rp.max_depth)) return false; // main.rs:59-61: the next ray_color call returns black (the caller keeps a NaN throughput alive in the pixel)
     r.ox = h.px, r.oy = h.py, r.oz = h.pz;
@@ -328,8 +332,14 @@ __global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : R
                 mat_type = int((h.meta >> 8) & 15u);
             }
             if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
-                const HitInfo hi = finalize_hit<false>(prims + (h.leaf & kLeafMask), frames, h.leaf >> kLeafBits, r, h.t);
-                if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
+                const DPrim *P = prims + (h.leaf & kLeafMask);
+                bool front;
+                if (!RICH && plain_rect_front_face(P, r, front)) { // a solid-colour rectangle light outside any wrapper: the emission needs the side only
+                    if (front) rad = texture_value<false>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, HitInfo());
+                } else {
+                    const HitInfo hi = finalize_hit<false>(P, frames, h.leaf >> kLeafBits, r, h.t);
+                    if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
+                }
                 ends = true;
             } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
                 if (!hit) rad = mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);

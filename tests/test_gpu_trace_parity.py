@@ -56,6 +56,56 @@ def test_closest_hit_matches_oracle(rt, oracle, gpu_ctx, name, n, extent):
     gsc.close()
 
 
+def _cornell_edge_points(rng, n):
+    """Points on the 12 edges of the Cornell room and of the rotated tall box (main.rs:425-435,451-494)."""
+    def box_edges(lo, hi, m):
+        corner = lo + (hi - lo) * rng.integers(0, 2, (m, 3))
+        axis = rng.integers(0, 3, m)
+        pts = corner.astype(np.float64)
+        pts[np.arange(m), axis] = lo[axis] + (hi[axis] - lo[axis]) * rng.random(m)
+        return pts
+    room = box_edges(np.zeros(3), np.full(3, 555.0), n // 2)
+    local = box_edges(np.zeros(3), np.array([165.0, 330.0, 165.0]), n - n // 2)
+    c, s = np.cos(np.radians(15.0)), np.sin(np.radians(15.0))  # hittable.rs:259-262 (object -> world), then Translate
+    box = np.stack([c * local[:, 0] + s * local[:, 2], local[:, 1], -s * local[:, 0] + c * local[:, 2]], axis=1) + np.array([265.0, 0.0, 295.0])
+    return np.concatenate([room, box])
+
+
+@pytest.mark.parametrize("name", ["cornel_box", "cornel_smoke"])
+def test_closest_hit_near_box_edges(rt, oracle, gpu_ctx, name):
+    """Rays aimed within 1e-7 .. 1e-1 of the edges of the room and of the box: where the flat scan's face groups
+    (one f32 slab computation names the entry and exit face of a box, kernels.cuh: closest_hit_flat) must fall back to
+    per-face candidates.  Same bars as the synthetic ray set."""
+    api = rt.api
+    n = 1 << 17
+    hs = api.HostScene(name, seed=1)
+    osc = oracle.OracleScene(hs.desc)
+    gsc = api.Scene(gpu_ctx, hs.desc)
+    rng = np.random.Generator(np.random.Philox(0xED6E))
+    target = _cornell_edge_points(rng, n)
+    v = rng.normal(size=(n, 3))
+    target += v / np.linalg.norm(v, axis=1, keepdims=True) * 10.0 ** rng.uniform(-7.0, -1.0, (n, 1))
+    origin = np.where(rng.random((n, 1)) < 0.75, 5.0 + 545.0 * rng.random((n, 3)), np.array([[278.0, 278.0, -800.0]]))
+    origin[n // 2:n // 2 + n // 8] = target[n // 2:n // 2 + n // 8] + np.array([[0.0, 0.0, -300.0]])  # axis-parallel rays
+    rays = np.zeros(n, dtype=api.RAY_DTYPE)
+    rays["origin"] = origin
+    rays["direction"] = (target - origin) * 10.0 ** rng.uniform(-2.5, 0.5, (n, 1))
+    rays["time"] = rng.random(n).astype(np.float32)
+    gp, gt, gn, gff, guv = gsc.trace_closest(rays, seed=7)
+    op, ot, on, off, ouv, amb = osc.trace_closest(rays, seed=7)
+    keep = amb == 0
+    assert keep.mean() > 0.9
+    bad = keep & (gp != op)
+    assert not bad.any(), f"{bad.sum()} primitive-id mismatches, first at ray {np.flatnonzero(bad)[:5]}: gpu {gp[bad][:5]} oracle {op[bad][:5]}"
+    hit = keep & (op >= 0)
+    assert hit.sum() > n // 2
+    rel_t = np.abs(gt[hit].astype(np.float64) - ot[hit]) / np.maximum(np.abs(ot[hit]), 1e-30)
+    assert rel_t.max() <= 1e-5, f"hit distance off by {rel_t.max():.3e} relative"
+    assert np.abs(gn[hit].astype(np.float64) - on[hit]).max() <= 1e-5
+    assert (gff[hit] == off[hit]).all()
+    gsc.close()
+
+
 def test_trace_empty_and_tiny(rt, oracle, gpu_ctx):
     api = rt.api
     hs = api.HostScene("cornel_box", seed=1)

@@ -25,6 +25,10 @@ HOST_HDRS = ["host/rt1w.hpp", "host/scenes.hpp", "host/host_api.h", "../include/
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # f32 division and square root (shading, pdfs, f32 screens: never the f64 intersection solve) as MUFU + multiply
+    # (2 ulp) instead of the IEEE sequences with their slow-path calls: the wave kernels are bound by their
+    # instruction-cache footprint
+    "-prec-div=false", "-prec-sqrt=false",
     "-Xcompiler", "-fPIC,-O3,-Wall", "-cudart", "static", "--shared", "-ccbin", GXX,
 ]
 
@@ -45,7 +49,7 @@ def build_product(force=False, extra_flags=(), variant=None):
     """variant: builds _build/variant_<variant>.so with extra -D flags (tuning sweeps; select with RT1W_LIB)."""
     os.makedirs(OUT, exist_ok=True)
     target = os.path.join(OUT, "librt1w.so" if not variant else f"variant_{variant}.so")
-    deps = [os.path.join(PKG, p) for p in CUDA_SRCS + CUDA_HDRS]
+    deps = [os.path.join(PKG, p) for p in CUDA_SRCS + CUDA_HDRS] + [os.path.abspath(__file__)]
     if force or _stale(target, deps):
         _run([NVCC] + NVCC_FLAGS + list(extra_flags) + ["-o", target] + CUDA_SRCS)
     return target

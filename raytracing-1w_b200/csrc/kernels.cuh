@@ -1027,6 +1027,7 @@ RT1W_DEV f3 scatter_lambertian(const SceneView &sc, const DLight *lights, const 
 
 RT1W_DEV f3 scatter_metal(const DMaterial &m, const Ray &r, const HitInfo &h, const Philox4 x, Rng &rng) { // material.rs:98-112
     const f3 reflected = reflect(normalize(mk3(r.dx, r.dy, r.dz)), h.normal);
+    if (m.fuzz == 0.0f) return reflected; // the reference still runs the sampler (material.rs:102) and multiplies it by zero
     return reflected + m.fuzz * random_in_unit_sphere(x, rng);
 }
 

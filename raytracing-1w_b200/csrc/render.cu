@@ -42,6 +42,10 @@ namespace rt1w {
 #define RT1W_PERSISTENT_MIN_BLOCKS 4 // persistent BVH wave kernel: more resident rays only thrash L1 on the big trees it is used for
 #endif
 constexpr int kWaveThreads = RT1W_WAVE_THREADS;
+#ifndef RT1W_FLAT_THREADS
+#define RT1W_FLAT_THREADS 128
+#endif
+constexpr int kFlatThreads = RT1W_FLAT_THREADS; // CTA size of the flat-scan wave kernel
 constexpr int kExtendThreads = kWaveThreads; // k_trace shares the traversal-stack geometry
 
 // Scattering material families, in the order their queues are laid out in a wave's thread index space.
@@ -51,20 +55,31 @@ static_assert(RT1W_MAT_LAMBERTIAN == 0 && RT1W_MAT_METAL == 1 && RT1W_MAT_DIELEC
 // Sorts the lanes of a warp into the per-material hit queues with ONE atomic instruction: lane q
 // reserves queue q's entries for the whole warp (Q_COUNT lanes, Q_COUNT addresses, one round trip),
 // then every lane fetches the base of its own destination with a shuffle.  dest < 0: nothing to append.
-RT1W_DEV uint32_t warp_sort_reserve(uint32_t *n_mat, int dest) {
+// Two halves, so that the caller can put independent work (the splat of the paths that end) between the atomic
+// and the first use of its result: the round trip to L2 was 40 % of the wave kernel's long-scoreboard stalls.
+struct QueueReservation {
+    uint32_t base; // lane q: start of the warp's entries in queue q
+    uint32_t mine; // lanes with the same destination as this one
+};
+RT1W_DEV QueueReservation warp_sort_begin(uint32_t *n_mat, int dest) {
     const int lane = threadIdx.x & 31;
-    uint32_t mine = 0, count_for_lane = 0;
+    QueueReservation res;
+    res.base = 0, res.mine = 0;
+    uint32_t count_for_lane = 0;
 #pragma unroll
     for (int q = 0; q < Q_COUNT; ++q) {
         if (q == RT1W_MAT_DIFFUSE_LIGHT) continue; // lights end the path inside the wave
         const unsigned m = __ballot_sync(0xffffffffu, dest == q);
-        if (dest == q) mine = m;
+        if (dest == q) res.mine = m;
         if (lane == q) count_for_lane = uint32_t(__popc(m));
     }
-    uint32_t base = 0;
-    if (count_for_lane) base = atomicAdd(&n_mat[lane], count_for_lane);
-    base = __shfl_sync(0xffffffffu, base, dest < 0 ? 0 : dest);
-    return base + __popc(mine & ((1u << lane) - 1u));
+    if (count_for_lane) res.base = atomicAdd(&n_mat[lane], count_for_lane);
+    return res;
+}
+RT1W_DEV uint32_t warp_sort_end(const QueueReservation &res, int dest) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t base = __shfl_sync(0xffffffffu, res.base, dest < 0 ? 0 : dest);
+    return base + __popc(res.mine & ((1u << lane) - 1u));
 }
 
 // A path ends: pixel += throughput * radiance.  A NaN product must reach the sum even when the
@@ -226,11 +241,11 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 // RICH: some texture is not a SolidColor (else checker / Perlin / image code is compiled out: a third of the kernel).
 template <bool FLAT, bool MEDIA, bool RICH>
-__global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) + (MEDIA ? 0 : 1))
+__global__ void __launch_bounds__(FLAT ? kFlatThreads : kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) + (MEDIA ? 0 : 1))
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
     // one static buffer: the staged primitive list + entry-distance table (FLAT) or the per-thread traversal stacks (BVH)
-    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kWaveThreads;
+    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kFlatThreads;
     __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kWaveThreads];
     __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
     __shared__ unsigned int s_traced;
@@ -302,6 +317,18 @@ __global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : R
                 const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
                 r = load_ray(in, j, c);
                 const HitRec hr = stream_load(in.h + j);
+#ifdef RT1W_PREFETCH
+                { // this thread's next work item, when it lies in the same queue: on its way to L2 while this one is processed
+                    const uint32_t jn = j + gridDim.x * blockDim.x;
+                    if (jn < (seg == 0 ? lay.cnt0 : (seg == 1 ? lay.cnt1 : (seg == 2 ? lay.cnt2 : lay.cnt3)))) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.a + jn));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.b + jn));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.c + jn));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.t + jn));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.h + jn));
+                    }
+                }
+#endif
                 skip_leaf = hr.leaf;
                 const float4 th4 = stream_load(in.t + j);
                 thr = mk3(th4.x, th4.y, th4.z);
@@ -316,7 +343,8 @@ __global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : R
 
         int dest = -1;
         HitRec h;
-        f3 rad = mk3(0.0f, 0.0f, 0.0f); // radiance the path ends on
+        int mat_type = RT1W_MAT_NONE;
+        bool hit = false;
         if (alive) { // extend: closest hit, then end the path or hand it to the material it landed on
             ++traced;
             MediumRng mr = {0, 0, 0, 0, 0};
@@ -324,34 +352,35 @@ __global__ void __launch_bounds__(kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : R
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
-            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kWaveThreads, skip_leaf, h.t, h.leaf)
-                                  : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
-            int mat_type = RT1W_MAT_NONE;
+            hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kFlatThreads, skip_leaf, h.t, h.leaf)
+                       : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
             if (hit) {
                 h.meta = FLAT ? s_flat[0].prims[h.leaf & kLeafMask].meta : __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
                 mat_type = int((h.meta >> 8) & 15u);
             }
-            if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
-                const DPrim *P = prims + (h.leaf & kLeafMask);
-                bool front;
-                if (!RICH && plain_rect_front_face(P, r, front)) { // a solid-colour rectangle light outside any wrapper: the emission needs the side only
-                    if (front) rad = texture_value<false>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, HitInfo());
-                } else {
-                    const HitInfo hi = finalize_hit<false>(P, frames, h.leaf >> kLeafBits, r, h.t);
-                    if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
-                }
-                ends = true;
-            } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
-                if (!hit) rad = mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
-                ends = true;
+            if (mat_type == RT1W_MAT_DIFFUSE_LIGHT || mat_type == RT1W_MAT_NONE) ends = true; // main.rs:110-115
+            else dest = mat_type;
+        }
+        __syncwarp();
+        // the queue entries are reserved while the paths that end here reach their pixels (the atomic's round trip is hidden)
+        const QueueReservation res = warp_sort_begin(ctr->n_mat[nxt], dest);
+        f3 rad = mk3(0.0f, 0.0f, 0.0f); // radiance the path ends on
+        if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
+            const DPrim *P = prims + (h.leaf & kLeafMask);
+            bool front;
+            if (!RICH && plain_rect_front_face(P, r, front)) { // a solid-colour rectangle light outside any wrapper: the emission needs the side only
+                if (front) rad = texture_value<false>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, HitInfo());
             } else {
-                dest = mat_type;
+                const HitInfo hi = finalize_hit<false>(P, frames, h.leaf >> kLeafBits, r, h.t);
+                if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
             }
+        } else if (alive && !hit) { // main.rs:113-115: a miss sees the background; `impl Material for ()` (material.rs:68) ends on zero radiance
+            rad = mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
         }
         // the one place a path reaches its pixel; zero radiance still has to deliver a NaN / inf throughput (splat)
         if (ends && (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f || !finite3(thr))) splat(a, c.pixel, thr, rad);
         __syncwarp();
-        const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
+        const uint32_t e = warp_sort_end(res, dest);
         if (dest >= 0) { // ray + path state + hit go to the queue of the material the ray landed on
             const RayQueue &out = a.pool.mat[parity ^ 1][dest];
             stream_store(out.a + e, make_double2(r.ox, r.oy));
@@ -577,7 +606,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
                 }
             }
             __syncwarp();
-            const uint32_t e = warp_sort_reserve(ctr->n_mat[nxt], dest);
+            const uint32_t e = warp_sort_end(warp_sort_begin(ctr->n_mat[nxt], dest), dest);
             if (dest >= 0) {
                 const RayQueue &out = a.pool.mat[parity ^ 1][dest];
                 stream_store(out.a + e, make_double2(r.ox, r.oy));
@@ -702,8 +731,9 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
                                            : (media ? (rich ? k_wave<false, true, true> : k_wave<false, true, false>)
                                                     : (rich ? k_wave<false, false, true> : k_wave<false, false, false>));
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
+    const int threads = flat ? kFlatThreads : kWaveThreads;
     int per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWaveThreads, perlin_bytes)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
     const int blocks = sm_count * (per_sm > 0 ? per_sm : 1);
 
     // profiling mode: one event before every launch and one at the end of the chunk
@@ -749,7 +779,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         for (int k = 0; k < poll_every; ++k, ++wave) {
             const int slot = int(wave % 3), parity = int(wave & 1);
             mark(K_WAVE);
-            kernel<<<blocks, kWaveThreads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            kernel<<<blocks, threads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
             ++ws.launches;
         }
         mark(-1);

@@ -372,8 +372,9 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
             const int fg = face_group[scan[k]];
             if (fg >= 0) { // every face slot carries the group's box, its planes moved outward by the f32 error of a tagged plane
                            // distance: 2^-23 |o| + (2^-22 + 2^-21) |plane - o| in space units, below 2e-6 reach for origins
-                           // within 2 x reach (see scan_pad).  A rectangle is hit ON its plane: its +-0.0001 slab is not needed.
-                const double face_pad = 3e-6 * reach;
+                           // within 2 x reach (see scan_pad), + the f32 frame transform of pass 1 (3 roundings of reach-sized terms).
+                           // A rectangle is hit ON its plane: its +-0.0001 slab is not needed.
+                const double face_pad = 4e-6 * reach;
                 double pad = 0.0; // distance of the padded planes from the true faces after rounding outward
                 for (int c = 0; c < 3; ++c) {
                     lo[c] = std::nextafter(float(group_box[fg][c] - face_pad), -std::numeric_limits<float>::infinity());

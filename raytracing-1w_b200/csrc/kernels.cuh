@@ -470,6 +470,7 @@ struct FlatScene {
     float4 lo[kFlatMax], hi[kFlatMax]; // scan order: padded f32 bounds in the frame of the group; lo.w = leaf (int bits)
     float4 sphere[kFlatMax];           // scan order, sphere groups: centre and radius in f32
     DFrame frames[kFlatMaxFrames];
+    float4 frame_f[kFlatMaxFrames][2]; // f32 copy of the rigid part for pass 1: (sin, cos, b.x, b.y), (b.z, -, -, -)
     // scan-order groups: group g = boxes [group_end[g-1], group_end[g]) in frame group_frame[g] (-1 = world).
     // group_kind[g]: G_BOXES one box per primitive; G_SPHERES plain spheres, screened by an f32 discriminant on top of
     // the box; G_FACES rectangles that are faces of ONE box (every slot of the group carries that box): face_slot[g][f]
@@ -493,6 +494,11 @@ RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the 
     for (int w = threadIdx.x; w < n * int(sizeof(DPrim) / 4); w += blockDim.x) dst[w] = src[w];
     src = reinterpret_cast<const uint32_t *>(sc.frames), dst = reinterpret_cast<uint32_t *>(fs.frames);
     for (int w = threadIdx.x; w < sc.n_frames * int(sizeof(DFrame) / 4); w += blockDim.x) dst[w] = src[w];
+    for (int i = threadIdx.x; i < sc.n_frames; i += blockDim.x) {
+        const DFrame &f = sc.frames[i];
+        fs.frame_f[i][0] = make_float4(float(f.sin_t), float(f.cos_t), float(f.bx), float(f.by));
+        fs.frame_f[i][1] = make_float4(float(f.bz), 0.0f, 0.0f, 0.0f);
+    }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float4 lo = sc.prim_boxes[3 * i], hi = sc.prim_boxes[3 * i + 1];
         fs.lo[i] = lo, fs.hi[i] = hi;
@@ -528,10 +534,10 @@ RT1W_DEV void flat_stage(const SceneView &sc, FlatScene &fs) { // call with the 
 struct SlabRayF {
     float ix, iy, iz, ox, oy, oz; // 1/d and -o/d
 };
-RT1W_DEV SlabRayF slab_ray(double ox, double oy, double oz, float dx, float dy, float dz) {
+RT1W_DEV SlabRayF slab_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
     SlabRayF s;
     s.ix = rcp_capped(dx), s.iy = rcp_capped(dy), s.iz = rcp_capped(dz);
-    s.ox = -__double2float_rn(ox) * s.ix, s.oy = -__double2float_rn(oy) * s.iy, s.oz = -__double2float_rn(oz) * s.iz;
+    s.ox = -ox * s.ix, s.oy = -oy * s.iy, s.oz = -oz * s.iz;
     return s;
 }
 constexpr float kTMinSlab = 0.000999f; // just below t_min: a box the ray leaves before t_min cannot hold an accepted root
@@ -570,15 +576,17 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
     const int n_groups = fs.n_groups;
     int k = 0, cur_frame = -2;
     SlabRayF s;
+    const float ofx = __double2float_rn(r.ox), ofy = __double2float_rn(r.oy), ofz = __double2float_rn(r.oz);
     for (int g = 0; g < n_groups; ++g) {
         const int frame = fs.group_frame[g], end = fs.group_end[g];
         if (frame != cur_frame) {
             cur_frame = frame;
             if (frame < 0) {
-                s = slab_ray(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
-            } else {
-                const LocalRay l = to_local(frame_xf(fs.frames, frame), r);
-                s = slab_ray(l.ox, l.oy, l.oz, float(l.dx), float(l.dy), float(l.dz));
+                s = slab_ray(ofx, ofy, ofz, r.dx, r.dy, r.dz);
+            } else { // hittable.rs:207,241-245 in f32: 1e-4 of error at Cornell coordinates, inside the box padding (api.cu)
+                const float4 f0 = fs.frame_f[frame][0], f1 = fs.frame_f[frame][1]; // sin, cos, b.x, b.y | b.z
+                s = slab_ray(fmaf(f0.y, ofx, fmaf(-f0.x, ofz, f0.z)), ofy + f0.w, fmaf(f0.x, ofx, fmaf(f0.y, ofz, f1.x)),
+                             fmaf(f0.y, r.dx, -f0.x * r.dz), r.dy, fmaf(f0.x, r.dx, f0.y * r.dz));
             }
         }
         const int kind = fs.group_kind[g];

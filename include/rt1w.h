@@ -254,6 +254,13 @@ rt1w_status rt1w_scene_get_prims(const rt1w_scene *scene, rt1w_flat_prim *out, i
  * rt1w_scene_get_prims would return after a create.  Used by tools and CPU tests. */
 rt1w_status rt1w_lower_prims(const rt1w_scene_desc *desc, rt1w_flat_prim *out, int32_t capacity, int32_t *n_out);
 
+/* Host-side only: the face groups the small-scene closest-hit scan forms over the lowered primitives - rectangles of
+ * one wrapper frame that are whole faces of a common box (the walls of a room, the six sides of aabox.rs:29-76) are
+ * tested with one slab computation.  Per primitive (rt1w_lower_prims order): group number or -1, and the face
+ * 2 * axis + (upper plane ? 1 : 0) with axis 0 = x (YZRect), 1 = y (XZRect), 2 = z (XYRect).  Used by CPU tests. */
+rt1w_status rt1w_lower_face_groups(const rt1w_scene_desc *desc, int32_t *group_of_prim, int32_t *face_of_prim, int32_t capacity,
+                                   int32_t *n_groups);
+
 /* Replaces the pixel loop + ray_color (main.rs:957-1001, 51-190).
  * out_rgb_sum: HOST buffer, width*height*3 floats, row 0 = top, per-pixel SUM
  *   over the rendered sample range (not yet divided by spp).

@@ -110,7 +110,7 @@ class HostSettings(C.Structure):
 # every entry point include/rt1w.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "rt1w_abi_version", "rt1w_last_error", "rt1w_context_create", "rt1w_context_destroy", "rt1w_scene_create",
-    "rt1w_scene_destroy", "rt1w_scene_get_info", "rt1w_scene_get_prims", "rt1w_lower_prims", "rt1w_render",
+    "rt1w_scene_destroy", "rt1w_scene_get_info", "rt1w_scene_get_prims", "rt1w_lower_prims", "rt1w_lower_face_groups", "rt1w_render",
     "rt1w_render_device", "rt1w_render_rgb8", "rt1w_trace_closest", "rt1w_resolve_rgb8", "rt1w_philox4x32",
 ]
 
@@ -145,6 +145,7 @@ def load_library():
     lib.rt1w_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
     lib.rt1w_scene_get_prims.argtypes = [vp, C.POINTER(FlatPrim), C.c_int32, C.POINTER(C.c_int32)]
     lib.rt1w_lower_prims.argtypes = [C.POINTER(SceneDesc), C.POINTER(FlatPrim), C.c_int32, C.POINTER(C.c_int32)]
+    lib.rt1w_lower_face_groups.argtypes = [C.POINTER(SceneDesc), vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     lib.rt1w_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     lib.rt1w_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     lib.rt1w_trace_closest.argtypes = [vp, vp, C.c_size_t, C.c_uint64, vp, vp, vp, vp, vp]
@@ -414,6 +415,17 @@ def lower_prims(desc):
     out = (FlatPrim * max(1, n.value))()
     _check(lib.rt1w_lower_prims(dp, out, n.value, C.byref(n)))
     return list(out)[: n.value]
+
+
+def lower_face_groups(desc):
+    """Host-side (no GPU): per lowered primitive the face group of the flat scan (-1: none) and its face; the group count."""
+    lib = load_library()
+    n_prims = len(lower_prims(desc))
+    dp = desc if isinstance(desc, C.POINTER(SceneDesc)) else C.pointer(desc)
+    group, face = np.full(max(1, n_prims), -1, dtype=np.int32), np.full(max(1, n_prims), -1, dtype=np.int32)
+    n_groups = C.c_int32(0)
+    _check(lib.rt1w_lower_face_groups(dp, group.ctypes.data, face.ctypes.data, n_prims, C.byref(n_groups)))
+    return group[:n_prims], face[:n_prims], n_groups.value
 
 
 # --------------------------------------------------------------------------- device objects

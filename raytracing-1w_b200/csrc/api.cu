@@ -237,6 +237,24 @@ rt1w_status rt1w_lower_prims(const rt1w_scene_desc *desc, rt1w_flat_prim *out, i
     return RT1W_OK;
 }
 
+rt1w_status rt1w_lower_face_groups(const rt1w_scene_desc *desc, int32_t *group_of_prim, int32_t *face_of_prim, int32_t capacity, int32_t *n_groups) {
+    LoweredScene low;
+    std::string err;
+    rt1w_status st = lower_scene(desc, low, err);
+    if (st != RT1W_OK) return fail(st, err);
+    std::vector<uint32_t> order(low.prims.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = uint32_t(i);
+    std::vector<int> group(low.prims.size(), -1), face(low.prims.size(), -1);
+    std::vector<std::array<double, 6>> boxes;
+    find_face_groups(low.prims, order, group, face, boxes);
+    for (int32_t i = 0; i < capacity && i < int32_t(low.prims.size()); ++i) {
+        if (group_of_prim) group_of_prim[i] = group[i];
+        if (face_of_prim) face_of_prim[i] = face[i];
+    }
+    if (n_groups) *n_groups = int32_t(boxes.size());
+    return RT1W_OK;
+}
+
 rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt1w_scene **out) {
     if (!ctx || !out) return fail(RT1W_ERR_INVALID, "null context or output pointer");
     *out = nullptr;

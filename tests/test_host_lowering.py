@@ -37,6 +37,25 @@ def test_cornel_box_lowering(rt, oracle):
     assert oracle.OracleScene(hs.desc).num_prims == 13
 
 
+def test_face_groups(rt):
+    """The flat scan's face groups (api.cu: find_face_groups): the five walls of the Cornell room and the six sides of
+    the box (aabox.rs:29-76 order: XY@z1, XY@z0, XZ@y1, XZ@y0, YZ@x1, YZ@x0) each share one slab computation."""
+    api = rt.api
+    hs = api.HostScene("cornel_box", seed=1)  # (the description lives as long as the host scene)
+    group, face, n = api.lower_face_groups(hs.desc)
+    assert n == 2
+    # prims: YZ@555, YZ@0, light, XZ@0, XZ@555, XY@555 (main.rs:451-494), box sides, sphere
+    assert list(group) == [0, 0, -1, 0, 0, 0, 1, 1, 1, 1, 1, 1, -1]
+    assert list(face) == [1, 0, -1, 2, 3, 5, 5, 4, 3, 2, 1, 0, -1]
+    hs = api.HostScene("cornel_smoke", seed=1)
+    group, face, n = api.lower_face_groups(hs.desc)
+    assert n == 1 and list(group[:6]) == [0, 0, -1, 0, 0, 0] and (group[6:] == -1).all()  # the smoke boxes are media, not rectangles
+    for name in ("two_spheres", "simple_light", "earth"):  # fewer than three faces of a common box: no group
+        hs = api.HostScene(name, seed=1)
+        group, face, n = api.lower_face_groups(hs.desc)
+        assert n == 0 and (group == -1).all()
+
+
 @pytest.mark.parametrize("name,n_prims", [("two_spheres", 2), ("two_perlin_spheres", 2), ("earth", 1), ("simple_light", 3),
                                           ("cornel_smoke", 8), ("final_scene", 3409)])
 def test_scene_primitive_counts(rt, oracle, name, n_prims):

@@ -313,7 +313,8 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     if (use_lbvh) {
         RT1W_CUDA(cudaSetDevice(ctx->device));
         std::vector<float> boxes(6 * n);
-        for (size_t i = 0; i < n; ++i) conservative_box(dev[i].bbox_min, dev[i].bbox_max, &boxes[6 * i], &boxes[6 * i + 3]);
+        const double pad = traversal_pad(bmin.data(), bmax.data(), n);
+        for (size_t i = 0; i < n; ++i) conservative_box(dev[i].bbox_min, dev[i].bbox_max, &boxes[6 * i], &boxes[6 * i + 3], pad);
         int depth = 0;
         cudaError_t e = build_lbvh(boxes.data(), n, ctx->stream, &d_lbvh_nodes, &n_bvh_nodes, bvh.prim_order, &depth);
         if (e != cudaSuccess) return fail_cuda("device BVH build", e);

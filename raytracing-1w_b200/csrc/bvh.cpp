@@ -34,10 +34,11 @@ struct Builder {
     int max_depth = 0;
     double cost = 0.0;
     double root_area = 1.0;
+    double pad = 0.0; // extra padding of every node box: the rounding of the traversal's FMA-form slab test (kernels.cuh: slab)
 
     // Conservative f32 bounds: round outward and pad, so that f32 slab arithmetic never culls
     // a primitive the f64 reference would reach.
-    void store_box(BvhNode32 &n, const Box &b) const { conservative_box(b.lo, b.hi, n.min, n.max); }
+    void store_box(BvhNode32 &n, const Box &b) const { conservative_box(b.lo, b.hi, n.min, n.max, pad); }
 
     void make_leaf(uint32_t node, uint32_t first, uint32_t count, const Box &b, int depth) {
         store_box(nodes[node], b);
@@ -126,6 +127,12 @@ struct Builder {
 
 } // namespace
 
+double traversal_pad(const double *bmin, const double *bmax, size_t n) {
+    double reach = 0.0;
+    for (size_t i = 0; i < 3 * n; ++i) reach = std::max(reach, std::max(std::fabs(bmin[i]), std::fabs(bmax[i])));
+    return 1e-6 * reach;
+}
+
 void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3], double extra_pad) {
     for (int k = 0; k < 3; ++k) {
         double ext = std::max(hi[k] - lo[k], std::max(std::fabs(lo[k]), std::fabs(hi[k])));
@@ -147,6 +154,7 @@ void build_sah_bvh(const double *bmin, const double *bmax, size_t n, int max_lea
     b.centroid.resize(3 * n);
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) b.centroid[3 * i + k] = 0.5 * (bmin[3 * i + k] + bmax[3 * i + k]);
+    b.pad = traversal_pad(bmin, bmax, n);
     b.build(0, 0, uint32_t(n), 0);
     out.depth = b.max_depth;
     out.sah_cost = b.cost;

@@ -25,6 +25,9 @@ struct BvhBuildResult {
 
 // Conservative f32 bounds of an f64 box: padded and rounded outward so that f32 slab arithmetic never
 // culls a primitive the f64 solve would reach.  out = {min.xyz, max.xyz}.
+// Extra padding of the traversal's node boxes: 1e-6 of the largest coordinate of the scene.  The FMA-form slab test
+// rounds by 2^-24 (|o| + |plane - o|) in space units; covered for ray origins up to ~5 x that coordinate away.
+double traversal_pad(const double *bmin, const double *bmax, size_t n);
 void conservative_box(const double lo[3], const double hi[3], float out_min[3], float out_max[3], double extra_pad = 0.0);
 
 // bmin/bmax: n x 3 doubles (world-space bounds of the lowered primitives).

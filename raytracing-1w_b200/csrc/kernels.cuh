@@ -326,15 +326,17 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
 // ------------------------------------------------------------------------------------------
 // extend: closest hit over the flat SAH BVH (replaces BVHNode::hit, bvh.rs:25-50)
 // ------------------------------------------------------------------------------------------
+// The node test in the FMA form t = plane * (1/d) - o * (1/d), |1/d| capped at 1e18 (rcp_capped) so that an axis the ray
+// is parallel to yields finite distances of the right sign.  The rounding of the form - 2^-24 (|o| + |plane - o|) in space
+// units - is covered by the padding of the node boxes (bvh.cpp: conservative_box with 1e-6 of the scene's reach on top).
 struct SlabRay {
-    float ox, oy, oz, ix, iy, iz;
+    float ix, iy, iz, ox, oy, oz; // 1/d and -o/d
 };
 
 RT1W_DEV bool slab(const float4 lo, const float4 hi, const SlabRay &s, float tmax, float &tnear) {
-    const float ax = (lo.x - s.ox) * s.ix, bx = (hi.x - s.ox) * s.ix;
-    const float ay = (lo.y - s.oy) * s.iy, by = (hi.y - s.oy) * s.iy;
-    const float az = (lo.z - s.oz) * s.iz, bz = (hi.z - s.oz) * s.iz;
-    // fminf/fmaxf drop NaNs (0 * inf on an axis-parallel ray grazing a slab plane)
+    const float ax = fmaf(lo.x, s.ix, s.ox), bx = fmaf(hi.x, s.ix, s.ox);
+    const float ay = fmaf(lo.y, s.iy, s.oy), by = fmaf(hi.y, s.iy, s.oy);
+    const float az = fmaf(lo.z, s.iz, s.oz), bz = fmaf(hi.z, s.iz, s.oz);
     const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
     float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
     tf = tf * 1.0000005f; // keep the f32 test conservative w.r.t. the f64 primitive solve
@@ -361,8 +363,8 @@ struct Trav {
 };
 
 RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, Trav &T) {
-    T.s.ox = float(r.ox), T.s.oy = float(r.oy), T.s.oz = float(r.oz);
-    T.s.ix = 1.0f / r.dx, T.s.iy = 1.0f / r.dy, T.s.iz = 1.0f / r.dz;
+    T.s.ix = rcp_capped(r.dx), T.s.iy = rcp_capped(r.dy), T.s.iz = rcp_capped(r.dz);
+    T.s.ox = -__double2float_rn(r.ox) * T.s.ix, T.s.oy = -__double2float_rn(r.oy) * T.s.iy, T.s.oz = -__double2float_rn(r.oz) * T.s.iz;
     T.best = CUDART_INF, T.bestf = CUDART_INF_F, T.best_leaf = -1, T.sp = 0;
     const float4 n0 = __ldg(sc.nodes), n1 = __ldg(sc.nodes + 1);
     float tn;

@@ -1,8 +1,8 @@
 // kernels.cuh — device code of the wavefront path tracer (sm_100a).
 //
 // Everything the reference does per ray inside `ray_color` (main.rs:51-190) lives here as
-// __device__ functions; render.cu wraps them into the wavefront kernels
-// (generate / extend / shade_<material>) and the closest-hit parity kernel.
+// __device__ functions; render.cu wraps them into the fused wave kernels (scatter / start paths,
+// closest hit, regroup per material) and the closest-hit parity kernel.
 //
 // Precision policy (DESIGN.md "Precision"): the reference is f64 throughout (main.rs:1).
 //   * BVH node slab tests: f32 on conservatively padded boxes (bvh.cpp store_box).
@@ -35,7 +35,7 @@ constexpr int kStackLocal = 64 - RT1W_STACK_SMEM; // overflow entries (local mem
 struct SceneView {
     const float4 *nodes;       // 2 x float4 per node
     const DPrim *prims;        // leaf order
-    const float4 *prim_boxes;  // flat scenes: 2 x float4 per primitive in SCAN order (see FlatScene), else nullptr
+    const float4 *prim_boxes;  // flat scenes: 3 x float4 per primitive in SCAN order (see flat_stage), else nullptr
     const int32_t *prim_id;    // leaf index -> primitive id (DFS order of the description)
     const DFrame *frames;
     const DMaterial *materials;

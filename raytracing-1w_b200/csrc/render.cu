@@ -317,18 +317,6 @@ __global__ void __launch_bounds__(FLAT ? kFlatThreads : kWaveThreads, (FLAT ? RT
                 const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
                 r = load_ray(in, j, c);
                 const HitRec hr = stream_load(in.h + j);
-#ifdef RT1W_PREFETCH
-                { // this thread's next work item, when it lies in the same queue: on its way to L2 while this one is processed
-                    const uint32_t jn = j + gridDim.x * blockDim.x;
-                    if (jn < (seg == 0 ? lay.cnt0 : (seg == 1 ? lay.cnt1 : (seg == 2 ? lay.cnt2 : lay.cnt3)))) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.a + jn));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.b + jn));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.c + jn));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.t + jn));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(in.h + jn));
-                    }
-                }
-#endif
                 skip_leaf = hr.leaf;
                 const float4 th4 = stream_load(in.t + j);
                 thr = mk3(th4.x, th4.y, th4.z);

@@ -82,6 +82,14 @@ RT1W_DEV uint32_t warp_sort_end(const QueueReservation &res, int dest) {
     return base + __popc(res.mine & ((1u << lane) - 1u));
 }
 
+// Programmatic dependent launch (sm_90+): a wave kernel is launched while its predecessor still runs; everything
+// before this call must not touch what the predecessor writes.  Once the predecessor is complete the next wave may
+// start its own prologue.
+RT1W_DEV void grid_dependency_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // A path ends: pixel += throughput * radiance.  A NaN product must reach the sum even when the
 // radiance is zero: the reference turns a NaN pixel SUM into black (color.rs:14-21), and
 // `li / pdf` with pdf == 0 is NaN there whatever li is (main.rs:102).
@@ -258,6 +266,20 @@ __global__ void __launch_bounds__(FLAT ? kFlatThreads : kWaveThreads, (FLAT ? RT
     FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
     float *s_tn = reinterpret_cast<float *>(s_raw + sizeof(FlatScene)); // entry distances, [primitive][thread]
 
+    // Scene tables into shared memory first: they do not depend on the previous wave, so with programmatic dependent
+    // launch (render_waves) this part runs while the previous wave drains.
+    if (FLAT) flat_stage(a.sc, s_flat[0]);
+    const DPerlin *perlins = a.sc.perlins;
+    if (RICH && perlin_in_smem) {
+        const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+        perlins = reinterpret_cast<const DPerlin *>(s_dyn);
+    }
+    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
+    grid_dependency_wait(); // the previous wave's queues and counters are complete and visible from here on
+
     Counters *ctr = a.pool.ctr;
     const int nxt = slot == 2 ? 0 : slot + 1, clr = nxt == 2 ? 0 : nxt + 1;
     // the thread index space of the wave: [lambertian hits | metal | dielectric | isotropic | new paths], each hit
@@ -285,16 +307,6 @@ __global__ void __launch_bounds__(FLAT ? kFlatThreads : kWaveThreads, (FLAT ? RT
         l.gen_t0 = uint32_t(path0 / a.rp.tile_paths), l.gen_w0 = uint32_t(path0 - (unsigned long long)l.gen_t0 * a.rp.tile_paths); // see generate_ray
         s_layout = l;
     }
-    if (FLAT) flat_stage(a.sc, s_flat[0]);
-    const DPerlin *perlins = a.sc.perlins;
-    if (RICH && perlin_in_smem) {
-        const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
-        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-        perlins = reinterpret_cast<const DPerlin *>(s_dyn);
-    }
-    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
     __syncthreads();
 
     const DPrim *prims = FLAT ? s_flat[0].prims : a.sc.prims;
@@ -433,6 +445,18 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     __shared__ unsigned int s_traced, s_next;
     __shared__ WaveLayout s_layout;
 
+    // scene tables first (independent of the previous wave: overlaps its tail under programmatic dependent launch)
+    const DPerlin *perlins = a.sc.perlins;
+    if (perlin_in_smem) {
+        const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+        perlins = reinterpret_cast<const DPerlin *>(s_dyn);
+    }
+    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
+    grid_dependency_wait(); // the previous wave's queues and counters are complete and visible from here on
+
     Counters *ctr = a.pool.ctr;
     const int nxt = slot == 2 ? 0 : slot + 1, clr = nxt == 2 ? 0 : nxt + 1;
     uint32_t total;
@@ -464,15 +488,6 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     const uint32_t my_blocks = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
     if (my_blocks == 0u) return;
 
-    const DPerlin *perlins = a.sc.perlins;
-    if (perlin_in_smem) {
-        const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
-        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
-        perlins = reinterpret_cast<const DPerlin *>(s_dyn);
-    }
-    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
     __syncthreads();
 
     const volatile WaveLayout &lay = s_layout;
@@ -723,6 +738,13 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
     const int blocks = sm_count * (per_sm > 0 ? per_sm : 1);
+    // every wave may start (scene tables -> shared memory) while the wave before it drains: programmatic dependent launch
+    cudaLaunchAttribute launch_attr[1];
+    launch_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    launch_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t launch = {};
+    launch.gridDim = dim3(unsigned(blocks)), launch.blockDim = dim3(unsigned(threads)), launch.dynamicSmemBytes = perlin_bytes, launch.stream = stream;
+    launch.attrs = launch_attr, launch.numAttrs = 1;
 
     // profiling mode: one event before every launch and one at the end of the chunk
     struct Mark {
@@ -767,7 +789,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         for (int k = 0; k < poll_every; ++k, ++wave) {
             const int slot = int(wave % 3), parity = int(wave & 1);
             mark(K_WAVE);
-            kernel<<<blocks, threads, perlin_bytes, stream>>>(args, slot, parity, perlin_in_smem);
+            if ((e = cudaLaunchKernelEx(&launch, kernel, args, slot, parity, perlin_in_smem)) != cudaSuccess) break;
             ++ws.launches;
         }
         mark(-1);

@@ -33,7 +33,7 @@ namespace rt1w {
 #define RT1W_WAVE_THREADS 128
 #endif
 #ifndef RT1W_FLAT_MIN_BLOCKS
-#define RT1W_FLAT_MIN_BLOCKS 5 // CTAs per SM of the flat-scan wave kernel with media; one more (80 registers, no spills) without
+#define RT1W_FLAT_MIN_BLOCKS 5 // CTAs per SM of the flat-scan wave kernel with media (128 threads, 96 registers)
 #endif
 #ifndef RT1W_BVH_MIN_BLOCKS
 #define RT1W_BVH_MIN_BLOCKS 5 // lockstep BVH wave kernel with media; one more without
@@ -43,9 +43,13 @@ namespace rt1w {
 #endif
 constexpr int kWaveThreads = RT1W_WAVE_THREADS;
 #ifndef RT1W_FLAT_THREADS
-#define RT1W_FLAT_THREADS 128
+#define RT1W_FLAT_THREADS 256 // medium-free flat-scan wave kernel: 3 CTAs of 256 threads per SM (80 registers) beat 6 of 128 by 1.4 %
 #endif
-constexpr int kFlatThreads = RT1W_FLAT_THREADS; // CTA size of the flat-scan wave kernel
+// CTA size and CTAs per SM of the wave kernel variants (the launch uses the same functions)
+__host__ __device__ constexpr int wave_threads(bool flat, bool media) { return flat && !media ? RT1W_FLAT_THREADS : kWaveThreads; }
+__host__ __device__ constexpr int wave_min_blocks(bool flat, bool media) {
+    return flat ? (media ? RT1W_FLAT_MIN_BLOCKS : 6 * 128 / RT1W_FLAT_THREADS) : RT1W_BVH_MIN_BLOCKS + (media ? 0 : 1);
+}
 constexpr int kExtendThreads = kWaveThreads; // k_trace shares the traversal-stack geometry
 
 // Scattering material families, in the order their queues are laid out in a wave's thread index space.
@@ -249,11 +253,12 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 // RICH: some texture is not a SolidColor (else checker / Perlin / image code is compiled out: a third of the kernel).
 template <bool FLAT, bool MEDIA, bool RICH>
-__global__ void __launch_bounds__(FLAT ? kFlatThreads : kWaveThreads, (FLAT ? RT1W_FLAT_MIN_BLOCKS : RT1W_BVH_MIN_BLOCKS) + (MEDIA ? 0 : 1))
+__global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLAT, MEDIA))
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
     // one static buffer: the staged primitive list + entry-distance table (FLAT) or the per-thread traversal stacks (BVH)
-    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kFlatThreads;
+    constexpr int kThreads = wave_threads(FLAT, MEDIA);
+    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kThreads;
     __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kWaveThreads];
     __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
     __shared__ unsigned int s_traced;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(FLAT ? kFlatThreads : kWaveThreads, (FLAT ? RT
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
-            hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kFlatThreads, skip_leaf, h.t, h.leaf)
+            hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kThreads, skip_leaf, h.t, h.leaf)
                        : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
             if (hit) {
                 h.meta = FLAT ? s_flat[0].prims[h.leaf & kLeafMask].meta : __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
@@ -734,7 +739,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
                                            : (media ? (rich ? k_wave<false, true, true> : k_wave<false, true, false>)
                                                     : (rich ? k_wave<false, false, true> : k_wave<false, false, false>));
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
-    const int threads = flat ? kFlatThreads : kWaveThreads;
+    const int threads = wave_threads(flat, media);
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
     const int blocks = sm_count * (per_sm > 0 ? per_sm : 1);

@@ -271,7 +271,10 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     std::vector<int32_t> dev_first_id;
     // scenes small enough for the flat scan keep their rectangles: the scan's frame-local boxes already cull five of a
     // box's six sides, and one code path for walls and box sides beats the shorter list (measured, Cornell box)
-    const bool merge_boxes = low.prims.size() > size_t(kFlatMax) || low.frames.size() > size_t(kFlatMaxFrames);
+    // ONE decision for both: a scene is either scanned with its rectangles kept (flat) or traversed with its boxes merged.
+    // (Deciding `flat` on the merged count would send P_BOX primitives into the scan, which compiles them out.)
+    const bool flat = low.prims.size() <= size_t(kFlatMax) && low.frames.size() <= size_t(kFlatMaxFrames);
+    const bool merge_boxes = !flat;
     for (size_t i = 0; i < low.prims.size();) {
         const rt1w_flat_prim &f0 = low.prims[i];
         bool is_box = merge_boxes && f0.kind == RT1W_NODE_XY_RECT && f0.node >= 0 && f0.node < desc->n_nodes && desc->nodes[f0.node].type == RT1W_NODE_AABOX &&
@@ -342,7 +345,6 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     }
     // Small scenes are scanned, not traversed (kernels.cuh: closest_hit_flat): one padded f32 box per primitive in
     // the primitive's own frame, listed frame by frame; lo.w = leaf index, hi.w = frame of the BOX (-1 = world).
-    const bool flat = n <= size_t(kFlatMax) && low.frames.size() <= size_t(kFlatMaxFrames);
     std::vector<float4> prim_boxes;
     if (flat) {
         // the scan's FMA-form slab test cancels o/d against plane/d (2^-23 |o| of absolute error per plane) and uses

@@ -56,7 +56,11 @@ struct Builder {
             cb.grow_point(&centroid[3 * p]);
         }
         if (depth == 0) root_area = std::max(b.area(), 1e-300);
-        if (count <= 1 || depth > 60) return make_leaf(node, first, count, b, depth);
+        if (count <= 1) return make_leaf(node, first, count, b, depth);
+        if (depth > 64) { // deeper than any traversal stack: stop recursing and report a depth the caller rejects (RT1W_ERR_UNSUPPORTED)
+            max_depth = 1000;
+            return make_leaf(node, first, 1, b, depth);
+        }
 
         // binned SAH over the three axes
         int best_axis = -1, best_split = -1;
@@ -150,6 +154,7 @@ void build_sah_bvh(const double *bmin, const double *bmax, size_t n, int max_lea
     out.nodes.reserve(2 * n + 2);
     out.nodes.push_back(BvhNode32{}); // root
     out.nodes.push_back(BvhNode32{}); // padding: children pairs start at even indices
+    if (max_leaf > 7) max_leaf = 7; // node_ref (kernels.cuh) keeps three bits of the leaf count
     Builder b{bmin, bmax, max_leaf, out.prim_order, out.nodes};
     b.centroid.resize(3 * n);
     for (size_t i = 0; i < n; ++i)

@@ -362,7 +362,15 @@ struct Trav {
     int sp;
 };
 
+#ifdef RT1W_COUNT_TRAV // measurement build (build.py --variant trav -DRT1W_COUNT_TRAV): rays, interior steps, primitive tests, warp-level interior steps
+static __device__ unsigned long long g_trav_counts[4];
+#define RT1W_TRAV_COUNT(k) atomicAdd(&g_trav_counts[k], 1ull)
+#else
+#define RT1W_TRAV_COUNT(k)
+#endif
+
 RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, Trav &T) {
+    RT1W_TRAV_COUNT(0);
     T.s.ix = rcp_capped(r.dx), T.s.iy = rcp_capped(r.dy), T.s.iz = rcp_capped(r.dz);
     T.s.ox = -__double2float_rn(r.ox) * T.s.ix, T.s.oy = -__double2float_rn(r.oy) * T.s.iy, T.s.oz = -__double2float_rn(r.oz) * T.s.iz;
     T.best = CUDART_INF, T.bestf = CUDART_INF_F, T.best_leaf = -1, T.sp = 0;
@@ -389,6 +397,10 @@ RT1W_DEV void trav_pop(Trav &T, const uint2 *stack, int stride, const uint2 *ove
 
 // one interior node: both children (one 64-byte pair) tested, nearer one first
 RT1W_DEV void trav_step_interior(const SceneView &sc, Trav &T, uint2 *stack, int stride, uint2 *overflow) {
+    RT1W_TRAV_COUNT(1);
+#ifdef RT1W_COUNT_TRAV
+    if (int(threadIdx.x & 31) == __ffs(int(__activemask())) - 1) RT1W_TRAV_COUNT(3);
+#endif
     const float4 *c = sc.nodes + 2 * T.ref;
     const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
     float tl, tr;
@@ -417,6 +429,7 @@ RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng 
         do {
             double t;
             int side = 0;
+            RT1W_TRAV_COUNT(2);
             if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + (first + i), int(first + i), r, T.best, mr, t, box_sides, side)) {
                 T.best = t, T.best_leaf = int(first + i) | (side << kLeafBits);
                 T.bestf = __double2float_ru(t);
@@ -716,6 +729,10 @@ struct HitInfo {
     bool front_face;
     int type; // PrimType
     uint32_t meta;
+    // where the record came from, so that an image texture can ask for a rectangle's (u, v) after the fact (rect_uv)
+    const DPrim *prim;
+    const DFrame *frames;
+    int side;
 };
 
 RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
@@ -726,6 +743,25 @@ RT1W_DEV void sphere_uv(f3 p, float &u, float &v) { // math.rs:67-71
     u = phi * (0.5f / kPiF), v = theta * (1.0f / kPiF);
 }
 
+// (u, v) of a hit on a rectangle or a box side (aarect.rs:60-61,98-99,166-167): the hit point's in-plane coordinates
+// normalised by the rectangle's intervals.  `type`: P_XY_RECT / P_XZ_RECT / P_YZ_RECT (for a P_BOX: the side's type),
+// (lx, ly, lz): the hit point in the leaf's own space.
+RT1W_DEV void rect_uv(const DPrim *P, int type, double lx, double ly, double lz, float &u, float &v) {
+    const double2 *w = reinterpret_cast<const double2 *>(P);
+    const double2 p01 = w[0], p23 = w[1];
+    const double a = type == P_YZ_RECT ? ly : lx, b = type == P_XY_RECT ? ly : lz;
+    double a0 = p01.x, a1 = p01.y, b0 = p23.x, b1 = p23.y;
+    if (int(P->meta & 15u) == P_BOX) { // the side's in-plane intervals out of the box corners
+        const int4 tail = *reinterpret_cast<const int4 *>(w + 3);
+        const double2 q01 = w[2];
+        const double x0 = p01.x, y0 = p01.y, z0 = p23.x, x1 = q01.x, y1 = q01.y, z1 = __hiloint2double(tail.y, tail.x);
+        a0 = type == P_YZ_RECT ? y0 : x0, a1 = type == P_YZ_RECT ? y1 : x1;
+        b0 = type == P_XY_RECT ? y0 : z0, b1 = type == P_XY_RECT ? y1 : z1;
+    }
+    u = float((a - a0) / (a1 - a0));
+    v = float((b - b0) / (b1 - b0));
+}
+
 // P: the primitive's record, frames: the wrapper frames (global memory or the flat scan's shared-memory copies).
 // `side`: which rectangle of a P_BOX was hit (see kLeafBits).
 template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const DPrim *P, const DFrame *frames, int side, const Ray &r, double t) {
@@ -734,63 +770,53 @@ template <bool WANT_UV> RT1W_DEV HitInfo finalize_hit(const DPrim *P, const DFra
     const int4 tail = *reinterpret_cast<const int4 *>(w + 3);
     h.meta = uint32_t(tail.z);
     h.type = int(h.meta & 15u);
+    h.prim = P, h.frames = frames, h.side = side;
     const bool box = h.type == P_BOX;
     if (box) h.type = P_XY_RECT + (side >> 1); // the sides come in the order XY, XY, XZ, XZ, YZ, YZ (aabox.rs:29-76)
     const int frame = tail.w;
     // ray.at(t) is invariant under the rigid wrappers; evaluate it once in world space
     h.px = r.ox + t * double(r.dx), h.py = r.oy + t * double(r.dy), h.pz = r.oz + t * double(r.dz);
     h.u = 0.0f, h.v = 0.0f;
-    if (h.type == P_MEDIUM_SPHERE || h.type == P_MEDIUM_BOX) { // constant_medium.rs:104-112
-        h.normal = h.n_out = mk3(1.0f, 0.0f, 0.0f);
-        h.front_face = true;
-        return h;
-    }
-    f3 n, ld; // outward normal and ray direction in the leaf's own space
-    double lx, ly, lz; // hit point in the leaf's own space
-    if (frame < 0) {
-        ld = mk3(r.dx, r.dy, r.dz);
-        lx = h.px, ly = h.py, lz = h.pz;
-    } else { // hittable.rs:207,241-245
-        const FrameXf *f = frame_xf(frames, frame);
-        const double s = f->sin_t, c = f->cos_t;
-        ld = mk3(float(c * double(r.dx) - s * double(r.dz)), r.dy, float(s * double(r.dx) + c * double(r.dz)));
-        lx = c * h.px - s * h.pz + f->bx, ly = h.py + f->by, lz = s * h.px + c * h.pz + f->bz;
-    }
+    f3 n; // outward normal in the leaf's own space, then the record's normal on its way out through the wrappers
     bool ff;
-    if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
-        const double2 p01 = w[0], p23 = w[1];
-        double cx = p01.x, cy = p01.y, cz = p23.x;
-        if (h.type == P_MOVING_SPHERE) {
-            const float4 f = *reinterpret_cast<const float4 *>(w + 2);
-            const double s = double((r.time - f.w) * __int_as_float(tail.x));
-            cx += s * double(f.x), cy += s * double(f.y), cz += s * double(f.z);
-        }
-        const float inv_r = 1.0f / float(p23.y); // sphere.rs:51
-        n = mk3(float(lx - cx) * inv_r, float(ly - cy) * inv_r, float(lz - cz) * inv_r);
-        if (WANT_UV) sphere_uv(n, h.u, h.v);
-        ff = dot(ld, n) < 0.0f; // HitRecord::new at the leaf, with the leaf-space ray (hittable.rs:30-35)
+    if (h.type == P_MEDIUM_SPHERE || h.type == P_MEDIUM_BOX) { // constant_medium.rs:98-106: a literal record, not HitRecord::new;
+        n = mk3(1.0f, 0.0f, 0.0f), ff = true;                  // the wrappers ABOVE the medium still rewrite it (the frame's ops)
+        h.n_out = n;
     } else {
-        float dn;
-        if (h.type == P_XY_RECT) n = mk3(0.0f, 0.0f, 1.0f), dn = ld.z;
-        else if (h.type == P_XZ_RECT) n = mk3(0.0f, 1.0f, 0.0f), dn = ld.y;
-        else n = mk3(1.0f, 0.0f, 0.0f), dn = ld.x;
-        if (WANT_UV) { // aarect.rs:60-61
-            const double2 p01 = w[0], p23 = w[1];
-            const double a = h.type == P_YZ_RECT ? ly : lx, b = h.type == P_XY_RECT ? ly : lz;
-            double a0 = p01.x, a1 = p01.y, b0 = p23.x, b1 = p23.y;
-            if (box) { // the side's in-plane intervals out of the box corners
-                const double2 q01 = w[2];
-                const double x0 = p01.x, y0 = p01.y, z0 = p23.x, x1 = q01.x, y1 = q01.y, z1 = __hiloint2double(tail.y, tail.x);
-                a0 = h.type == P_YZ_RECT ? y0 : x0, a1 = h.type == P_YZ_RECT ? y1 : x1;
-                b0 = h.type == P_XY_RECT ? y0 : z0, b1 = h.type == P_XY_RECT ? y1 : z1;
-            }
-            h.u = float((a - a0) / (a1 - a0));
-            h.v = float((b - b0) / (b1 - b0));
+        f3 ld;             // ray direction in the leaf's own space
+        double lx, ly, lz; // hit point in the leaf's own space
+        if (frame < 0) {
+            ld = mk3(r.dx, r.dy, r.dz);
+            lx = h.px, ly = h.py, lz = h.pz;
+        } else { // hittable.rs:207,241-245
+            const FrameXf *f = frame_xf(frames, frame);
+            const double s = f->sin_t, c = f->cos_t;
+            ld = mk3(float(c * double(r.dx) - s * double(r.dz)), r.dy, float(s * double(r.dx) + c * double(r.dz)));
+            lx = c * h.px - s * h.pz + f->bx, ly = h.py + f->by, lz = s * h.px + c * h.pz + f->bz;
         }
-        ff = dn < 0.0f;
+        if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
+            const double2 p01 = w[0], p23 = w[1];
+            double cx = p01.x, cy = p01.y, cz = p23.x;
+            if (h.type == P_MOVING_SPHERE) {
+                const float4 f = *reinterpret_cast<const float4 *>(w + 2);
+                const double s = double((r.time - f.w) * __int_as_float(tail.x));
+                cx += s * double(f.x), cy += s * double(f.y), cz += s * double(f.z);
+            }
+            const float inv_r = 1.0f / float(p23.y); // sphere.rs:51
+            n = mk3(float(lx - cx) * inv_r, float(ly - cy) * inv_r, float(lz - cz) * inv_r);
+            if (WANT_UV) sphere_uv(n, h.u, h.v);
+            ff = dot(ld, n) < 0.0f; // HitRecord::new at the leaf, with the leaf-space ray (hittable.rs:30-35)
+        } else {
+            float dn;
+            if (h.type == P_XY_RECT) n = mk3(0.0f, 0.0f, 1.0f), dn = ld.z;
+            else if (h.type == P_XZ_RECT) n = mk3(0.0f, 1.0f, 0.0f), dn = ld.y;
+            else n = mk3(1.0f, 0.0f, 0.0f), dn = ld.x;
+            if (WANT_UV) rect_uv(P, h.type, lx, ly, lz, h.u, h.v); // aarect.rs:60-61
+            ff = dn < 0.0f;
+        }
+        h.n_out = n;
+        if (!ff) n = -n;
     }
-    h.n_out = n;
-    if (!ff) n = -n;
     if (frame >= 0) {
         const DFrame *f = frames + frame;
         const int n_ops = f->n_ops;
@@ -891,8 +917,19 @@ template <bool RICH> RT1W_DEV f3 texture_value(const SceneView &sc, const DPerli
         return mk3(s, s, s);
     }
     case RT1W_TEX_IMAGE: { // texture.rs:67-89: nearest texel, (0,0) = top-left
+        // the shading paths build their records without (u, v) (finalize_hit<false>): only this texture reads them
         float u = h.u, v = h.v;
-        if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) sphere_uv(h.n_out, u, v);
+        if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
+            sphere_uv(h.n_out, u, v);
+        } else if (h.type == P_XY_RECT || h.type == P_XZ_RECT || h.type == P_YZ_RECT) { // a rectangle or a box side (aarect.rs:60-61)
+            double lx = h.px, ly = h.py, lz = h.pz;
+            const int frame = h.prim->frame;
+            if (frame >= 0) { // hittable.rs:207,241-245
+                const FrameXf *f = frame_xf(h.frames, frame);
+                lx = f->cos_t * h.px - f->sin_t * h.pz + f->bx, ly = h.py + f->by, lz = f->sin_t * h.px + f->cos_t * h.pz + f->bz;
+            }
+            rect_uv(h.prim, h.type, lx, ly, lz, u, v);
+        }
         u = fminf(fmaxf(u, 0.0f), 1.0f);
         v = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
         const int2 dim = sc.image_dims[t.table];

@@ -722,8 +722,7 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     const bool flat = args.sc.flat != 0;
     const bool media = (material_mask & (1 << RT1W_MAT_ISOTROPIC)) != 0;
     size_t perlin_bytes = size_t(args.sc.n_perlins) * sizeof(DPerlin);
-    const int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
-    if (!perlin_in_smem) perlin_bytes = 0;
+    int perlin_in_smem = perlin_bytes > 0 && perlin_bytes <= 40 * 1024;
     const int poll_every = 8;
     // grid: every CTA resident at once (SM count x occupancy); the kernel grid-strides over a device-side count
     using WaveKernel = void (*)(const RenderArgs, const int, const int, const int);
@@ -739,6 +738,22 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
                                            : (media ? (rich ? k_wave<false, true, true> : k_wave<false, true, false>)
                                                     : (rich ? k_wave<false, false, true> : k_wave<false, false, false>));
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
+    // The Perlin tables ride on top of the kernel's static shared memory: beyond 48 KB in total the kernel has to opt in,
+    // and a scene with more tables than fit reads them from global memory instead (perlin.rs:7-12 keeps them on the heap).
+    if (perlin_in_smem) {
+        cudaFuncAttributes fa;
+        int optin = 0, dev = 0;
+        if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t need = fa.sharedSizeBytes + perlin_bytes;
+        if (need > size_t(optin)) perlin_in_smem = 0;
+        else if (need > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(perlin_bytes)) != cudaSuccess) {
+            cudaGetLastError();
+            perlin_in_smem = 0;
+        }
+    }
+    if (!perlin_in_smem) perlin_bytes = 0;
     const int threads = wave_threads(flat, media);
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
@@ -832,6 +847,15 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         cudaMemcpyToSymbol(g_scan_counts, zero, sizeof(zero));
         std::fprintf(stderr, "[flat scan] rays %llu, candidates per ray %.3f, f64 solves per ray %.3f, solve iterations per warp of 32 rays %.3f\n", d[0],
                      double(d[1]) / double(d[0]), double(d[2]) / double(d[0]), 32.0 * double(d[3]) / double(d[0]));
+    }
+#endif
+#ifdef RT1W_COUNT_TRAV
+    if (!flat) {
+        unsigned long long d[4] = {0, 0, 0, 0}, zero[4] = {0, 0, 0, 0};
+        cudaMemcpyFromSymbol(d, g_trav_counts, sizeof(d));
+        cudaMemcpyToSymbol(g_trav_counts, zero, sizeof(zero));
+        std::fprintf(stderr, "[bvh] rays %llu, interior steps per ray %.2f, primitive tests per ray %.3f, lanes per warp-level interior step %.2f\n", d[0],
+                     double(d[1]) / double(d[0]), double(d[2]) / double(d[0]), double(d[1]) / double(d[3] ? d[3] : 1));
     }
 #endif
     return cudaSuccess;

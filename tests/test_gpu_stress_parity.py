@@ -1,0 +1,75 @@
+"""BASELINE.json config 5 - the synthetic stress scene (random spheres in a 2000^3 cube + 16 rectangle lights, SURVEY.md
+section 8d) - against the oracle: closest hits (north_star checks 1 and 2) and images (check 3), for both BVH builders
+(host binned SAH / device LBVH, `RT1W_BVH_BUILDER`) and both BVH wave kernels (`RT1W_FLAG_BVH_LOCKSTEP / _PERSISTENT`).
+Reference semantics under test: bvh.rs:25-50 (closest hit over the tree), sphere.rs:24-63, aarect.rs:84-110.
+
+Sizes: 2 * 10^5 spheres for the full comparison; the full 10^6 of the config with a smaller ray set and image (the
+oracle's median-split tree over a million spheres answers ~1000 rays per second and core).
+"""
+import numpy as np
+import pytest
+
+from common import check_render_parity, check_trace_parity, make_ray_set
+
+pytestmark = pytest.mark.gpu
+
+
+def _params_for(hs, width):
+    return lambda spp, begin, flags, clamp, seed: hs.params(width=width, spp=spp, sample_begin=begin, flags=flags, stat_clamp=clamp, seed=seed)
+
+
+@pytest.mark.parametrize("n_spheres,n_rays,width,spp", [(200_000, 1 << 17, 128, 64), (1_000_000, 1 << 14, 64, 32)])
+def test_stress_scene_matches_oracle(rt, oracle, gpu_ctx, monkeypatch, n_spheres, n_rays, width, spp):
+    api = rt.api
+    hs = api.HostScene("stress", seed=1, stress_spheres=n_spheres)
+    osc = oracle.OracleScene(hs.desc)
+    cam = hs.camera()
+    rays, trace_cache, render_cache = None, {}, {}
+    for builder in ("lbvh", "sah"):
+        monkeypatch.setenv("RT1W_BVH_BUILDER", builder)
+        gsc = api.Scene(gpu_ctx, hs.desc)
+        monkeypatch.delenv("RT1W_BVH_BUILDER")
+        info = gsc.info()
+        assert info.n_prims == n_spheres + 16
+        if rays is None:
+            rays = make_ray_set(api, hs, osc, gsc.prims(), n_rays)
+        # a sparse cloud: most rays of the uniform half leave the cube without a hit
+        check_trace_parity(gsc, osc, rays, min_hit_fraction=0.05, label=f"stress {n_spheres} spheres, {builder} tree", cache=trace_cache)
+        for flag in (api.FLAG_BVH_LOCKSTEP, api.FLAG_BVH_PERSISTENT):
+            if n_spheres > 500_000 and builder == "sah" and flag == api.FLAG_BVH_LOCKSTEP:
+                continue  # (the million-sphere renders are the slow part of the test; three of the four combinations do)
+            g_st, o_st = check_render_parity(api, gsc, osc, cam, _params_for(hs, width), spp, flags=flag, cache=render_cache)
+            print(f"[stress {n_spheres}, {builder}, flag {flag}] rays/path gpu {g_st.rays / g_st.paths:.3f} oracle {o_st.rays / o_st.paths:.3f}")
+        gsc.close()
+
+
+def test_stress_builders_and_kernels_agree(rt, gpu_ctx, monkeypatch):
+    """Same closest hits from both trees and the same image from both wave kernels (Philox draws are keyed by the path,
+    not by the traversal), at a size where every combination is cheap."""
+    api = rt.api
+    hs = api.HostScene("stress", seed=1, stress_spheres=300_000)
+    cam = hs.camera()
+    rng = np.random.Generator(np.random.Philox(5))
+    n = 1 << 17
+    rays = np.zeros(n, dtype=api.RAY_DTYPE)
+    rays["origin"] = rng.uniform(-1100.0, 1100.0, (n, 3))
+    v = rng.normal(size=(n, 3))
+    rays["direction"] = v / np.linalg.norm(v, axis=1, keepdims=True) * rng.uniform(0.5, 20.0, (n, 1))
+    out, imgs = {}, {}
+    for builder in ("lbvh", "sah"):
+        monkeypatch.setenv("RT1W_BVH_BUILDER", builder)
+        gsc = api.Scene(gpu_ctx, hs.desc)
+        monkeypatch.delenv("RT1W_BVH_BUILDER")
+        out[builder] = gsc.trace_closest(rays, seed=3)
+        for flag in (api.FLAG_BVH_LOCKSTEP, api.FLAG_BVH_PERSISTENT):
+            imgs[builder, flag] = gsc.render(cam, hs.params(width=160, spp=8, seed=2, flags=flag))
+        gsc.close()
+    a, b = out["lbvh"], out["sah"]
+    same = a[0] == b[0]
+    assert same.mean() > 0.9999  # (two spheres at the same distance within f64 rounding may resolve either way)
+    assert np.array_equal(a[1][same], b[1][same]) and np.array_equal(a[2][same], b[2][same])
+    ref_img, _, ref_st = imgs["sah", api.FLAG_BVH_LOCKSTEP]
+    for key, (img, _, st) in imgs.items():
+        assert st.rays == ref_st.rays, key
+        ok = np.isfinite(img) & np.isfinite(ref_img)
+        assert np.allclose(img[ok], ref_img[ok], rtol=1e-3, atol=1e-3), key

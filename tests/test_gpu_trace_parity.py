@@ -7,52 +7,57 @@ hit distance, normal and (u, v) must agree within 1e-5.
 import numpy as np
 import pytest
 
-from common import make_ray_set
+from common import check_trace_parity, make_ray_set
 
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # scene, rays, sampling box half-size around look_at (None = scene bounds)
-    ("cornel_box", 1 << 18, None),
-    ("cornel_smoke", 1 << 17, None),
-    ("simple_light", 1 << 16, 30.0),
-    ("two_spheres", 1 << 16, 30.0),
-    ("random_scene", 1 << 17, 15.0),
-    ("final_scene", 1 << 17, 700.0),
-    ("earth", 1 << 15, 10.0),
+    # scene, rays (SURVEY.md 8d asks for 2^20; the oracle's median-split trees answer the bigger scenes more slowly),
+    # sampling box half-size around look_at (None = scene bounds), aspect handed to Camera::new (None = the scene's own)
+    ("cornel_box", 1 << 20, None, None),
+    ("cornel_box", 1 << 18, None, 3840.0 / 2160.0),  # BASELINE config 4: the 16:9 camera sees past the room
+    ("cornel_smoke", 1 << 17, None, None),
+    ("simple_light", 1 << 16, 30.0, None),
+    ("two_spheres", 1 << 16, 30.0, None),
+    ("random_scene", 1 << 17, 15.0, None),
+    ("one_weekend", 1 << 17, 15.0, None),  # BASELINE config 2 in its One-Weekend flavour (static spheres)
+    ("final_scene", 1 << 17, 700.0, None),
+    ("earth", 1 << 15, 10.0, None),
 ]
 
 
-@pytest.mark.parametrize("name,n,extent", CASES)
-def test_closest_hit_matches_oracle(rt, oracle, gpu_ctx, name, n, extent):
+def _cornell_tie_reasons(rays, ot, amb):
+    """Why the oracle calls a Cornell-box ray ambiguous: the bottom of the box lies IN the floor (main.rs:425-435 puts it at
+    y = 0, main.rs:478-485 the floor too: a ray from above meets both at the same t and the reference's winner depends on
+    its random BVH order), an edge of the room, or a silhouette (a 1e-9-relative nudge of the ray changes the primitive)."""
+    a = amb != 0
+    p = rays["origin"][a].astype(np.float64) + np.where(np.isfinite(ot[a]), ot[a], 0.0)[:, None] * rays["direction"][a].astype(np.float64)
+    c, s = np.cos(np.radians(15.0)), np.sin(np.radians(15.0))
+    q = p - np.array([265.0, 0.0, 295.0])
+    loc = np.stack([c * q[:, 0] - s * q[:, 2], q[:, 1], s * q[:, 0] + c * q[:, 2]], axis=1)  # hittable.rs:241-245
+    eps = 1e-5
+    hit = np.isfinite(ot[a])
+    floor = hit & (np.abs(p[:, 1]) < eps * 555) & (loc[:, 0] > -eps * 165) & (loc[:, 0] < 165 * (1 + eps)) & (loc[:, 2] > -eps * 165) & (loc[:, 2] < 165 * (1 + eps))
+    room_edge = hit & ~floor & (((np.abs(p) < eps * 555) | (np.abs(p - 555) < eps * 555)).sum(axis=1) >= 2)
+    return int(floor.sum()), int(room_edge.sum()), int(a.sum() - floor.sum() - room_edge.sum())
+
+
+@pytest.mark.parametrize("name,n,extent,aspect", CASES)
+def test_closest_hit_matches_oracle(rt, oracle, gpu_ctx, name, n, extent, aspect):
     api = rt.api
     hs = api.HostScene(name, seed=1)
     osc = oracle.OracleScene(hs.desc)
     gsc = api.Scene(gpu_ctx, hs.desc)
     prims = gsc.prims()
     assert len(prims) == osc.num_prims
-    rays = make_ray_set(api, hs, osc, prims, n, extent)
-    seed = 0x5EED
-    gp, gt, gn, gff, guv = gsc.trace_closest(rays, seed=seed)
-    op, ot, on, off, ouv, amb = osc.trace_closest(rays, seed=seed)
-    keep = amb == 0
-    frac_amb = 1.0 - keep.mean()
-    assert frac_amb < 0.02, f"{frac_amb:.4f} of the rays are ambiguous: the ray set is badly conditioned"
-    bad = keep & (gp != op)
-    assert not bad.any(), f"{bad.sum()} primitive-id mismatches, first at ray {np.flatnonzero(bad)[:5]}: gpu {gp[bad][:5]} oracle {op[bad][:5]}"
-    hit = keep & (op >= 0)
-    assert hit.sum() > n // 10
-    rel_t = np.abs(gt[hit].astype(np.float64) - ot[hit]) / np.maximum(np.abs(ot[hit]), 1e-30)
-    assert rel_t.max() <= 1e-5, f"hit distance off by {rel_t.max():.3e} relative"
-    dn = np.abs(gn[hit].astype(np.float64) - on[hit]).max()
-    assert dn <= 1e-5, f"normal off by {dn:.3e}"
-    assert (gff[hit] == off[hit]).all()
-    du = np.abs(guv[hit, 0].astype(np.float64) - ouv[hit, 0])
-    du = np.minimum(du, 1.0 - du)  # u wraps at the atan2 branch cut (math.rs:69)
-    dv = np.abs(guv[hit, 1].astype(np.float64) - ouv[hit, 1])
-    assert max(du.max(), dv.max()) <= 2e-5
-    miss = keep & (op < 0)
-    assert np.isinf(gt[miss]).all()
+    rays = make_ray_set(api, hs, osc, prims, n, extent, aspect=aspect)
+    cache = {}
+    check_trace_parity(gsc, osc, rays, label=f"{name}{' 16:9' if aspect else ''}", cache=cache)
+    if name == "cornel_box":  # the ties have a name: say which, and that nothing else is excluded from the id comparison
+        _, ot, _, _, _, amb = cache["trace"]
+        floor, edge, silhouette = _cornell_tie_reasons(rays, ot, amb)
+        print(f"[trace parity] cornel_box ties: {floor} box bottom in the floor, {edge} room edges, {silhouette} silhouettes / grazing of {n} rays")
+        assert floor + edge + silhouette == int((amb != 0).sum()) and silhouette <= 2e-4 * n and edge <= 5e-4 * n
     gsc.close()
 
 

@@ -291,6 +291,30 @@ rt1w_status rt1w_render_rgb8(rt1w_scene *scene, const rt1w_camera *camera, const
 rt1w_status rt1w_trace_closest(rt1w_scene *scene, const rt1w_ray *rays, size_t n, uint64_t seed,
                                int32_t *prim_id, float *t, float *normal3, uint8_t *front_face, float *uv2);
 
+/* Pointwise parity hooks for the shading functions (test-only entry points, like rt1w_trace_closest): the device
+ * functions the wave kernels call, evaluated for n host inputs, so that a checker can hold them against the reference
+ * formulas value by value.  All buffers are HOST buffers.
+ *   rt1w_eval_light_pdf   light >= 0: `pdf_value(o, v)` of that entry of the light list (XZRect aarect.rs:119-138,
+ *                         Sphere sphere.rs:72-90, others 0 by the trait default hittable.rs:66-68); light < 0: the
+ *                         list's own `sum (1/n) pdf_value_i` (hittable.rs:144-150), i.e. HittablePdf::value (pdf.rs:47-49)
+ *   rt1w_eval_texture     `Texture::value(u, v, p)` (texture.rs:40-89); uv2 may be NULL (u = v = 0)
+ *   rt1w_eval_perlin      `Perlin::noise(p)` (turb_depth = 0, perlin.rs:46-72) or `turb(p, turb_depth)` (perlin.rs:74-86)
+ *   rt1w_eval_dielectric  `reflect`, `refract`, `reflectance(min(dot(-uv, n), 1), ratio)` (material.rs:94-96,114-125)
+ *   rt1w_eval_scatter     closest hit of ray i, then `Material::scatter` there as the render runs it for the path
+ *                         (pixel seed i, sample i & 0xffff, bounce 0): Philox key (i, seed lo), counter (i & 0xffff, 0,
+ *                         1 ^ (seed hi << 4), block).  material_type: rt1w_material_type of the hit or -1 (miss);
+ *                         dir3: the scattered direction (zero when the path ends); weight3: attenuation * scattering_pdf
+ *                         / pdf for scattering materials (main.rs:100-103), the emitted radiance for a DiffuseLight
+ *                         (material.rs:168-181); time: the scattered ray's time (main.rs:86: the hit's t after a
+ *                         Lambertian bounce).  Any output pointer may be NULL. */
+rt1w_status rt1w_eval_light_pdf(rt1w_scene *scene, int32_t light, const double *origin3, const float *dir3, size_t n, float *pdf);
+rt1w_status rt1w_eval_texture(rt1w_scene *scene, int32_t texture, const double *p3, const float *uv2, size_t n, float *rgb3);
+rt1w_status rt1w_eval_perlin(rt1w_scene *scene, int32_t table, int32_t turb_depth, const double *p3, size_t n, float *out);
+rt1w_status rt1w_eval_dielectric(rt1w_context *ctx, const float *unit_dir3, const float *normal3, const float *ratio, size_t n,
+                                 float *reflect3, float *refract3, float *reflectance);
+rt1w_status rt1w_eval_scatter(rt1w_scene *scene, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id,
+                              int32_t *material_type, float *dir3, float *weight3, float *time);
+
 /* `Color::into_sampled` + `Display for SampledColor` (color.rs:14-21,56-65):
  * NaN sum -> 0, mean, sqrt, clamp to [0,0.999], *256, truncate.  Host code. */
 void rt1w_resolve_rgb8(const float *rgb_sum, int32_t width, int32_t height, int32_t samples_per_pixel, uint8_t *out_rgb8);

@@ -112,6 +112,7 @@ ABI_SYMBOLS = [
     "rt1w_abi_version", "rt1w_last_error", "rt1w_context_create", "rt1w_context_destroy", "rt1w_scene_create",
     "rt1w_scene_destroy", "rt1w_scene_get_info", "rt1w_scene_get_prims", "rt1w_lower_prims", "rt1w_lower_face_groups", "rt1w_render",
     "rt1w_render_device", "rt1w_render_rgb8", "rt1w_trace_closest", "rt1w_resolve_rgb8", "rt1w_philox4x32",
+    "rt1w_eval_light_pdf", "rt1w_eval_texture", "rt1w_eval_perlin", "rt1w_eval_dielectric", "rt1w_eval_scatter",
 ]
 
 
@@ -154,6 +155,11 @@ def load_library():
     lib.rt1w_resolve_rgb8.restype = None
     lib.rt1w_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rt1w_philox4x32.restype = None
+    lib.rt1w_eval_light_pdf.argtypes = [vp, C.c_int32, vp, vp, C.c_size_t, vp]
+    lib.rt1w_eval_texture.argtypes = [vp, C.c_int32, vp, vp, C.c_size_t, vp]
+    lib.rt1w_eval_perlin.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
+    lib.rt1w_eval_dielectric.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp]
+    lib.rt1w_eval_scatter.argtypes = [vp, vp, C.c_size_t, C.c_uint64, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -435,6 +441,16 @@ class Context:
         self._h = C.c_void_p()
         _check(lib.rt1w_context_create(device_id, C.byref(self._h)))
 
+    def eval_dielectric(self, unit_dir, normal, ratio):
+        """Device `reflect`, `refract`, `reflectance` (material.rs:94-96,114-125) for n unit directions / normals / index ratios."""
+        uv, nn = np.ascontiguousarray(unit_dir, dtype=np.float32), np.ascontiguousarray(normal, dtype=np.float32)
+        rr = np.ascontiguousarray(ratio, dtype=np.float32)
+        n = rr.shape[0]
+        refl, refr, f = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.float32)
+        _check(load_library().rt1w_eval_dielectric(self._h, uv.ctypes.data, nn.ctypes.data, rr.ctypes.data, n, refl.ctypes.data, refr.ctypes.data,
+                                                   f.ctypes.data))
+        return refl, refr, f
+
     def close(self):
         if self._h:
             load_library().rt1w_context_destroy(self._h)
@@ -515,6 +531,38 @@ class Scene:
                                       uv.ctypes.data_as(C.c_void_p)))
         return prim, t, normal, ff, uv
 
+    # pointwise parity hooks (include/rt1w.h: rt1w_eval_*)
+    def eval_light_pdf(self, origins, dirs, light=-1):
+        o, v = np.ascontiguousarray(origins, dtype=np.float64), np.ascontiguousarray(dirs, dtype=np.float32)
+        n = o.shape[0]
+        out = np.empty(n, np.float32)
+        _check(load_library().rt1w_eval_light_pdf(self._h, light, o.ctypes.data, v.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def eval_texture(self, texture, points, uv=None):
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        n = p.shape[0]
+        uv = None if uv is None else np.ascontiguousarray(uv, dtype=np.float32)
+        out = np.empty((n, 3), np.float32)
+        _check(load_library().rt1w_eval_texture(self._h, texture, p.ctypes.data, None if uv is None else uv.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def eval_perlin(self, table, points, turb_depth=0):
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        out = np.empty(p.shape[0], np.float32)
+        _check(load_library().rt1w_eval_perlin(self._h, table, turb_depth, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def eval_scatter(self, rays, seed=0):
+        """-> prim_id, material_type, scattered direction, weight (or emitted radiance), scattered time."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        n = rays.shape[0]
+        prim, mat = np.empty(n, np.int32), np.empty(n, np.int32)
+        d, w, t = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.float32)
+        _check(load_library().rt1w_eval_scatter(self._h, rays.ctypes.data, n, seed, prim.ctypes.data, mat.ctypes.data, d.ctypes.data,
+                                                w.ctypes.data, t.ctypes.data))
+        return prim, mat, d, w, t
+
     def close(self):
         if self._h:
             load_library().rt1w_scene_destroy(self._h)
@@ -525,6 +573,13 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+
+def philox4x32(counter, key):
+    """One Philox4x32-10 block (rt1w_philox4x32): what the device draws for (counter, key)."""
+    c, k, o = (C.c_uint32 * 4)(*[int(x) & 0xFFFFFFFF for x in counter]), (C.c_uint32 * 2)(*[int(x) & 0xFFFFFFFF for x in key]), (C.c_uint32 * 4)()
+    load_library().rt1w_philox4x32(c, k, o)
+    return list(o)
 
 
 def resolve_rgb8(rgb_sum, spp):

@@ -136,6 +136,28 @@ template <class T> cudaError_t upload(const std::vector<T> &v, T **out) {
     return e;
 }
 
+struct DeviceArena { // device copies of host arrays for one hook call; freed on scope exit
+    std::vector<void *> ptrs;
+    cudaError_t err = cudaSuccess;
+    template <class T> T *alloc(size_t count) {
+        void *p = nullptr;
+        if (err == cudaSuccess) err = cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+        if (p) ptrs.push_back(p);
+        return static_cast<T *>(p);
+    }
+    template <class T> T *upload(const T *host, size_t count, cudaStream_t stream) {
+        T *d = alloc<T>(count);
+        if (err == cudaSuccess && host && count) err = cudaMemcpyAsync(d, host, sizeof(T) * count, cudaMemcpyHostToDevice, stream);
+        return d;
+    }
+    template <class T> void download(T *host, const T *dev, size_t count, cudaStream_t stream) {
+        if (err == cudaSuccess && host && count) err = cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, stream);
+    }
+    ~DeviceArena() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+};
+
 } // namespace
 
 struct rt1w_context {
@@ -157,6 +179,7 @@ struct rt1w_scene {
     rt1w_scene_info info{};
     SceneView view{};
     int material_mask = 0;
+    int n_textures = 0;
     // device allocations
     float4 *d_nodes = nullptr;
     DPrim *d_prims = nullptr;
@@ -479,6 +502,7 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     for (const DTexture &t : low.textures)
         if (t.type != RT1W_TEX_SOLID) v.rich_textures = 1;
     s->material_mask = low.material_mask;
+    s->n_textures = int(low.textures.size());
     s->prims = low.prims;
     s->info.n_prims = int32_t(low.prims.size()), s->info.n_bvh_nodes = int32_t(n_bvh_nodes), s->info.n_frames = int32_t(low.frames.size());
     s->info.n_lights = int32_t(low.lights.size()), s->info.bvh_depth = bvh.depth, s->info.material_mask = low.material_mask;
@@ -668,6 +692,98 @@ rt1w_status rt1w_trace_closest(rt1w_scene *scene, const rt1w_ray *rays, size_t n
     if (normal3) RT1W_CUDA(cudaMemcpyAsync(normal3, b.normal, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (uv2) RT1W_CUDA(cudaMemcpyAsync(uv2, b.uv, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (front_face) RT1W_CUDA(cudaMemcpyAsync(front_face, b.ff, n, cudaMemcpyDeviceToHost, ctx->stream));
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+// ---- pointwise parity hooks (tests only) ----
+rt1w_status rt1w_eval_light_pdf(rt1w_scene *scene, int32_t light, const double *origin3, const float *dir3, size_t n, float *pdf) {
+    if (!scene || ((!origin3 || !dir3 || !pdf) && n)) return fail(RT1W_ERR_INVALID, "null argument");
+    if (light >= scene->view.n_lights || (light < 0 && scene->view.n_lights == 0)) return fail(RT1W_ERR_INVALID, "light index out of range");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    DeviceArena a;
+    const double *d_o = a.upload(origin3, 3 * n, ctx->stream);
+    const float *d_v = a.upload(dir3, 3 * n, ctx->stream);
+    float *d_out = a.alloc<float>(n);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(eval_light_pdf_launch(scene->view, light, d_o, d_v, n, d_out, ctx->stream));
+    a.download(pdf, d_out, n, ctx->stream);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_eval_texture(rt1w_scene *scene, int32_t texture, const double *p3, const float *uv2, size_t n, float *rgb3) {
+    if (!scene || ((!p3 || !rgb3) && n)) return fail(RT1W_ERR_INVALID, "null argument");
+    if (texture < 0 || texture >= scene->n_textures) return fail(RT1W_ERR_INVALID, "texture id out of range");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    DeviceArena a;
+    const double *d_p = a.upload(p3, 3 * n, ctx->stream);
+    const float *d_uv = uv2 ? a.upload(uv2, 2 * n, ctx->stream) : nullptr;
+    float *d_out = a.alloc<float>(3 * n);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(eval_texture_launch(scene->view, texture, 0, 0, d_p, d_uv, n, d_out, ctx->stream));
+    a.download(rgb3, d_out, 3 * n, ctx->stream);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_eval_perlin(rt1w_scene *scene, int32_t table, int32_t turb_depth, const double *p3, size_t n, float *out) {
+    if (!scene || ((!p3 || !out) && n)) return fail(RT1W_ERR_INVALID, "null argument");
+    if (table < 0 || table >= scene->view.n_perlins || turb_depth < 0) return fail(RT1W_ERR_INVALID, "perlin table id out of range");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    DeviceArena a;
+    const double *d_p = a.upload(p3, 3 * n, ctx->stream);
+    float *d_out = a.alloc<float>(n);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(eval_texture_launch(scene->view, -1, table, turb_depth, d_p, nullptr, n, d_out, ctx->stream));
+    a.download(out, d_out, n, ctx->stream);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_eval_dielectric(rt1w_context *ctx, const float *unit_dir3, const float *normal3, const float *ratio, size_t n, float *reflect3,
+                                 float *refract3, float *reflectance) {
+    if (!ctx || ((!unit_dir3 || !normal3 || !ratio) && n)) return fail(RT1W_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    DeviceArena a;
+    const float *d_uv = a.upload(unit_dir3, 3 * n, ctx->stream), *d_n = a.upload(normal3, 3 * n, ctx->stream), *d_r = a.upload(ratio, n, ctx->stream);
+    float *d_refl = a.alloc<float>(3 * n), *d_refr = a.alloc<float>(3 * n), *d_f = a.alloc<float>(n);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(eval_dielectric_launch(d_uv, d_n, d_r, n, d_refl, d_refr, d_f, ctx->stream));
+    a.download(reflect3, d_refl, 3 * n, ctx->stream), a.download(refract3, d_refr, 3 * n, ctx->stream), a.download(reflectance, d_f, n, ctx->stream);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_eval_scatter(rt1w_scene *scene, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, int32_t *material_type, float *dir3,
+                              float *weight3, float *time) {
+    if (!scene || (!rays && n)) return fail(RT1W_ERR_INVALID, "null argument");
+    if (n >= (size_t(1) << 32)) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^32-1 rays in one call");
+    rt1w_context *ctx = scene->ctx;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    DeviceArena a;
+    const rt1w_ray *d_rays = a.upload(rays, n, ctx->stream);
+    int32_t *d_prim = a.alloc<int32_t>(n), *d_leaf = a.alloc<int32_t>(n), *d_mat = a.alloc<int32_t>(n);
+    double *d_t = a.alloc<double>(n);
+    float *d_dir = a.alloc<float>(3 * n), *d_w = a.alloc<float>(3 * n), *d_time = a.alloc<float>(n);
+    RT1W_CUDA(a.err);
+    RT1W_CUDA(trace_closest_launch(scene->view, d_rays, n, seed, d_prim, nullptr, nullptr, nullptr, nullptr, ctx->stream, d_leaf, d_t));
+    RT1W_CUDA(eval_scatter_launch(scene->view, d_rays, d_leaf, d_t, n, seed, d_mat, d_dir, d_w, d_time, ctx->stream));
+    a.download(prim_id, d_prim, n, ctx->stream), a.download(material_type, d_mat, n, ctx->stream);
+    a.download(dir3, d_dir, 3 * n, ctx->stream), a.download(weight3, d_w, 3 * n, ctx->stream), a.download(time, d_time, n, ctx->stream);
+    RT1W_CUDA(a.err);
     RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
     return RT1W_OK;
 }

@@ -921,7 +921,7 @@ template <bool RICH> RT1W_DEV f3 texture_value(const SceneView &sc, const DPerli
         float u = h.u, v = h.v;
         if (h.type == P_SPHERE || h.type == P_MOVING_SPHERE) {
             sphere_uv(h.n_out, u, v);
-        } else if (h.type == P_XY_RECT || h.type == P_XZ_RECT || h.type == P_YZ_RECT) { // a rectangle or a box side (aarect.rs:60-61)
+        } else if (h.prim != nullptr && (h.type == P_XY_RECT || h.type == P_XZ_RECT || h.type == P_YZ_RECT)) { // a rectangle or a box side (aarect.rs:60-61)
             double lx = h.px, ly = h.py, lz = h.pz;
             const int frame = h.prim->frame;
             if (frame >= 0) { // hittable.rs:207,241-245

@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant__ SceneView sc, const rt1w_ray *__restrict__ rays, const size_t n,
                                                           const uint32_t seed_lo, const uint32_t seed_hi, int32_t *prim_id, float *t_out,
-                                                          float *normal3, uint8_t *front_face, float *uv2) {
+                                                          float *normal3, uint8_t *front_face, float *uv2, int32_t *leaf_out, double *t64_out) {
     __shared__ uint2 s_stack[kStackSmem * kExtendThreads];
     __shared__ FlatScene s_flat;
     float *s_tn = reinterpret_cast<float *>(s_stack); // the flat scan's entry-distance table shares the stack space
@@ -671,6 +671,98 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
         }
         if (front_face) front_face[i] = hit ? uint8_t(h.front_face) : uint8_t(0);
         if (uv2) uv2[2 * i] = hit ? h.u : 0.0f, uv2[2 * i + 1] = hit ? h.v : 0.0f;
+        if (leaf_out) leaf_out[i] = hit ? leaf : -1; // (the shading hooks below continue from here)
+        if (t64_out) t64_out[i] = hit ? t : CUDART_INF;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pointwise parity hooks for the shading functions (rt1w.h: rt1w_eval_*): the device functions the wave kernels
+// call, one thread per input, so that tests can hold them against the reference's formulas value by value
+// ------------------------------------------------------------------------------------------
+// `[T]: Hittable::pdf_value` over the light list (hittable.rs:144-150) or one light's own (aarect.rs:119-138, sphere.rs:72-90)
+__global__ void __launch_bounds__(256) k_eval_light_pdf(const __grid_constant__ SceneView sc, const int light, const double *__restrict__ o3,
+                                                        const float *__restrict__ v3, const size_t n, float *__restrict__ out) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const f3 v = mk3(v3[3 * i], v3[3 * i + 1], v3[3 * i + 2]);
+        float pdf = 0.0f;
+        if (light >= 0) {
+            pdf = light_pdf_value(sc.lights[light], o3[3 * i], o3[3 * i + 1], o3[3 * i + 2], v);
+        } else {
+            const float wl = 1.0f / float(sc.n_lights);
+            for (int l = 0; l < sc.n_lights; ++l) pdf += wl * light_pdf_value(sc.lights[l], o3[3 * i], o3[3 * i + 1], o3[3 * i + 2], v);
+        }
+        out[i] = pdf;
+    }
+}
+
+// Texture::value(u, v, p) (texture.rs:40-89) / Perlin::noise, turb (perlin.rs:46-106; depth 0 = noise)
+__global__ void __launch_bounds__(256) k_eval_texture(const __grid_constant__ SceneView sc, const int texture, const int perlin_table, const int turb_depth,
+                                                      const double *__restrict__ p3, const float *__restrict__ uv2, const size_t n,
+                                                      float *__restrict__ out) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        if (texture < 0) {
+            const DPerlin *tab = sc.perlins + perlin_table;
+            out[i] = turb_depth > 0 ? perlin_turb(tab, p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], turb_depth) : perlin_noise(tab, p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]);
+            continue;
+        }
+        HitInfo h;
+        h.px = p3[3 * i], h.py = p3[3 * i + 1], h.pz = p3[3 * i + 2];
+        h.u = uv2 ? uv2[2 * i] : 0.0f, h.v = uv2 ? uv2[2 * i + 1] : 0.0f;
+        h.type = P_XY_RECT, h.prim = nullptr, h.frames = nullptr, h.side = 0; // prim == nullptr: (u, v) are given
+        h.normal = h.n_out = mk3(0.0f, 0.0f, 1.0f), h.front_face = true, h.meta = 0u;
+        const f3 c = texture_value<true>(sc, sc.perlins, texture, h);
+        out[3 * i] = c.x, out[3 * i + 1] = c.y, out[3 * i + 2] = c.z;
+    }
+}
+
+// reflect, refract, reflectance (material.rs:94-96,114-125) on unit directions
+__global__ void __launch_bounds__(256) k_eval_dielectric(const float *__restrict__ uv3, const float *__restrict__ n3, const float *__restrict__ ratio,
+                                                         const size_t n, float *__restrict__ reflect3, float *__restrict__ refract3,
+                                                         float *__restrict__ reflectance_out) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const f3 uv = mk3(uv3[3 * i], uv3[3 * i + 1], uv3[3 * i + 2]), nn = mk3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]);
+        const f3 a = reflect(uv, nn), b = refract(uv, nn, ratio[i]);
+        reflect3[3 * i] = a.x, reflect3[3 * i + 1] = a.y, reflect3[3 * i + 2] = a.z;
+        refract3[3 * i] = b.x, refract3[3 * i + 1] = b.y, refract3[3 * i + 2] = b.z;
+        reflectance_out[i] = reflectance(fminf(dot(-uv, nn), 1.0f), ratio[i]);
+    }
+}
+
+// Material::scatter at the closest hit of ray i (found by k_trace: leaf, t) - the same `scatter` the wave kernels run, for
+// path (pixel seed i, sample i & 0xffff, bounce 0).  A hit that ends the path reports what it emits instead.
+__global__ void __launch_bounds__(kExtendThreads) k_eval_scatter(const __grid_constant__ RenderArgs a, const rt1w_ray *__restrict__ rays,
+                                                                 const int32_t *__restrict__ leaf_in, const double *__restrict__ t_in, const size_t n,
+                                                                 int32_t *__restrict__ material_out, float *__restrict__ dir3,
+                                                                 float *__restrict__ weight3, float *__restrict__ time_out) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const rt1w_ray in = rays[i];
+        Ray r;
+        r.ox = in.origin[0], r.oy = in.origin[1], r.oz = in.origin[2];
+        r.dx = in.direction[0], r.dy = in.direction[1], r.dz = in.direction[2];
+        r.time = in.time;
+        const int leaf = leaf_in[i];
+        int mat_type = -1;
+        f3 w = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);
+        if (leaf >= 0) {
+            HitRec hr;
+            hr.t = t_in[i], hr.leaf = leaf, hr.meta = a.sc.prims[leaf & kLeafMask].meta;
+            mat_type = int((hr.meta >> 8) & 15u);
+            if (mat_type == RT1W_MAT_LAMBERTIAN || mat_type == RT1W_MAT_METAL || mat_type == RT1W_MAT_DIELECTRIC || mat_type == RT1W_MAT_ISOTROPIC) {
+                RayC c;
+                c.dz = r.dz, c.time = r.time, c.state = (uint32_t(i) & 0xffffu) << 8, c.pixel = uint32_t(i);
+                w = mk3(1.0f, 1.0f, 1.0f);
+                scatter<true, true>(mat_type, a, a.sc.prims, a.sc.frames, a.sc.perlins, a.sc.lights, r, hr, c, w);
+                d = mk3(r.dx, r.dy, r.dz);
+            } else if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181
+                const HitInfo hi = finalize_hit<false>(a.sc.prims + (leaf & kLeafMask), a.sc.frames, leaf >> kLeafBits, r, hr.t);
+                if (hi.front_face) w = texture_value<true>(a.sc, a.sc.perlins, a.sc.materials[hr.meta >> 12].texture, hi);
+            }
+        }
+        material_out[i] = mat_type;
+        dir3[3 * i] = d.x, dir3[3 * i + 1] = d.y, dir3[3 * i + 2] = d.z;
+        weight3[3 * i] = w.x, weight3[3 * i + 1] = w.y, weight3[3 * i + 2] = w.z;
+        time_out[i] = r.time;
     }
 }
 
@@ -883,11 +975,46 @@ cudaError_t resolve_launch(const float *d_rgb_sum, size_t n_values, int samples_
 }
 
 cudaError_t trace_closest_launch(const SceneView &sc, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, float *t,
-                                 float *normal3, uint8_t *front_face, float *uv2, cudaStream_t stream) {
+                                 float *normal3, uint8_t *front_face, float *uv2, cudaStream_t stream, int32_t *leaf, double *t64) {
     if (n == 0) return cudaSuccess;
     const size_t want = (n + kExtendThreads - 1) / kExtendThreads;
     const int blocks = int(want < 148 * 16 ? want : 148 * 16);
-    k_trace<<<blocks, kExtendThreads, 0, stream>>>(sc, rays, n, uint32_t(seed), uint32_t(seed >> 32), prim_id, t, normal3, front_face, uv2);
+    k_trace<<<blocks, kExtendThreads, 0, stream>>>(sc, rays, n, uint32_t(seed), uint32_t(seed >> 32), prim_id, t, normal3, front_face, uv2, leaf, t64);
+    return cudaGetLastError();
+}
+
+static int eval_blocks(size_t n, int threads) {
+    const size_t want = (n + threads - 1) / threads;
+    return int(want < 148 * 8 ? want : 148 * 8);
+}
+
+cudaError_t eval_light_pdf_launch(const SceneView &sc, int light, const double *o3, const float *v3, size_t n, float *pdf, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_eval_light_pdf<<<eval_blocks(n, 256), 256, 0, stream>>>(sc, light, o3, v3, n, pdf);
+    return cudaGetLastError();
+}
+
+cudaError_t eval_texture_launch(const SceneView &sc, int texture, int perlin_table, int turb_depth, const double *p3, const float *uv2, size_t n,
+                                float *out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_eval_texture<<<eval_blocks(n, 256), 256, 0, stream>>>(sc, texture, perlin_table, turb_depth, p3, uv2, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t eval_dielectric_launch(const float *uv3, const float *n3, const float *ratio, size_t n, float *reflect3, float *refract3,
+                                   float *reflectance, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_eval_dielectric<<<eval_blocks(n, 256), 256, 0, stream>>>(uv3, n3, ratio, n, reflect3, refract3, reflectance);
+    return cudaGetLastError();
+}
+
+cudaError_t eval_scatter_launch(const SceneView &sc, const rt1w_ray *rays, const int32_t *leaf, const double *t64, size_t n, uint64_t seed,
+                                int32_t *material, float *dir3, float *weight3, float *time_out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    RenderArgs a = {};
+    a.sc = sc;
+    a.rp.sample_begin = 0, a.rp.n_samples = 1 << 16, a.rp.max_depth = 50, a.rp.seed_lo = uint32_t(seed), a.rp.seed_hi = uint32_t(seed >> 32);
+    k_eval_scatter<<<eval_blocks(n, kExtendThreads), kExtendThreads, 0, stream>>>(a, rays, leaf, t64, n, material, dir3, weight3, time_out);
     return cudaGetLastError();
 }
 

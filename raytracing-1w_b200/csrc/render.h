@@ -66,8 +66,19 @@ struct WaveStats {
 cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_ctr, cudaStream_t stream, int sm_count, WaveStats &ws);
 
 // Closest-hit parity kernel (rt1w_trace_closest).  All pointers are device pointers; outputs may be null.
+// leaf / t64 (nullable): the hit as the kernels carry it (leaf | side << 28, f64 distance), input of eval_scatter_launch.
 cudaError_t trace_closest_launch(const SceneView &sc, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, float *t,
-                                 float *normal3, uint8_t *front_face, float *uv2, cudaStream_t stream);
+                                 float *normal3, uint8_t *front_face, float *uv2, cudaStream_t stream, int32_t *leaf = nullptr,
+                                 double *t64 = nullptr);
+
+// Pointwise parity hooks (rt1w.h: rt1w_eval_*); all pointers are device pointers.
+cudaError_t eval_light_pdf_launch(const SceneView &sc, int light, const double *o3, const float *v3, size_t n, float *pdf, cudaStream_t stream);
+cudaError_t eval_texture_launch(const SceneView &sc, int texture, int perlin_table, int turb_depth, const double *p3, const float *uv2, size_t n,
+                                float *out, cudaStream_t stream);
+cudaError_t eval_dielectric_launch(const float *uv3, const float *n3, const float *ratio, size_t n, float *reflect3, float *refract3,
+                                   float *reflectance, cudaStream_t stream);
+cudaError_t eval_scatter_launch(const SceneView &sc, const rt1w_ray *rays, const int32_t *leaf, const double *t64, size_t n, uint64_t seed,
+                                int32_t *material, float *dir3, float *weight3, float *time_out, cudaStream_t stream);
 
 // Device-side image resolve (color.rs:14-21,56-65): width*height*3 radiance sums -> 8-bit channels.
 cudaError_t resolve_launch(const float *d_rgb_sum, size_t n_values, int samples_per_pixel, uint8_t *d_rgb8, cudaStream_t stream);

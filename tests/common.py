@@ -139,7 +139,11 @@ def check_render_parity(api, gsc, osc, cam, make_params, spp, stat_clamp=20.0, f
     rmse_ga = np.sqrt(np.mean((img_g - img_a) ** 2.0))
     rmse_ab = np.sqrt(np.mean((img_a - img_b) ** 2.0))
     assert rmse_ga <= 1.15 * rmse_ab + 0.5, f"RMSE gpu-oracle {rmse_ga:.2f} vs oracle-oracle {rmse_ab:.2f} (8-bit levels)"
-    assert abs(gm.mean() - am.mean()) <= 0.02 * am.mean() + 1e-4, f"image mean gpu {gm.mean():.5f} oracle {am.mean():.5f}"
+    # whole-image mean within 2 % (+ 4 sigma of the two estimates: scenes lit by rarely-found lights, like the stress scene,
+    # have image means that are themselves noisy at test sizes)
+    sigma_mean = np.sqrt((gv + av).sum() / spp) / gv.size
+    assert abs(gm.mean() - am.mean()) <= 0.02 * am.mean() + 4.0 * sigma_mean + 1e-4, \
+        f"image mean gpu {gm.mean():.5f} oracle {am.mean():.5f} (sigma of the difference {sigma_mean:.5f})"
     rpp_g, rpp_o = g_st.rays / g_st.paths, oa_st.rays / oa_st.paths
     assert abs(rpp_g - rpp_o) <= 0.02 * rpp_o, f"rays/path gpu {rpp_g:.3f} oracle {rpp_o:.3f}"
     return g_st, oa_st

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RT1W_ABI_VERSION 1
+#define RT1W_ABI_VERSION 2
 
 typedef enum rt1w_status {
     RT1W_OK = 0,
@@ -236,9 +236,39 @@ int32_t rt1w_abi_version(void);
 /* Message of the most recent failure on this thread. */
 const char *rt1w_last_error(void);
 
-/* One context per process per GPU (`device_id` as in cudaSetDevice). */
+/* One context per process per GPU (`device_id` as in cudaSetDevice); several GPUs: see "Multi-GPU" below. */
 rt1w_status rt1w_context_create(int32_t device_id, rt1w_context **out);
 void rt1w_context_destroy(rt1w_context *ctx);
+
+/* ---- Multi-GPU -------------------------------------------------------------------------
+ * The sample loop has no cross-pixel or cross-sample state (main.rs:957-993), so the path shards by SAMPLE RANGE: the
+ * scene is replicated, rank r of n renders the r-th of n contiguous parts of [sample_begin, sample_end) of every pixel
+ * (rt1w_shard_sample_range; the Philox counter carries the global sample index, so the image does not depend on n up to
+ * fp32 summation order), and the partial radiance sums meet in ONE exchange step: ncclReduce(sum, fp32, 3*W*H) to rank
+ * 0 on the render streams, over NVLink.  NCCL is bound at run time (libnccl.so.2; a copy the host process has already
+ * loaded is shared); single-GPU use needs none.
+ *
+ * A context that belongs to a communicator makes EVERY render call (rt1w_render, rt1w_render_device, rt1w_render_rgb8)
+ * collective: all ranks call with the same arguments, each renders its share, rank 0 receives the image (the other
+ * ranks' output pointers may be NULL; after rt1w_render_device their buffers hold their own partial sums).
+ * rt1w_render_stats then counts this rank's paths and rays (multi-process) or all devices' (multi-device context), and
+ * render_ms includes the reduce.
+ *
+ *  (a) one process, n devices - what the reference's single `main` would use:
+ *        rt1w_context_create_multi(ids, n, &ctx);  rt1w_scene_create(ctx, ...);  rt1w_render(scene, ...);
+ *      The context owns one sub-context, render stream and host thread per device (rank i = device_ids[i]);
+ *      rt1w_scene_create commits the scene on all of them in parallel; the handles are used exactly like single-GPU ones.
+ *  (b) one process per device (MPI / torchrun style): rank 0 calls rt1w_comm_unique_id, the host side ships the id
+ *      to the other ranks (any transport), and every rank calls rt1w_context_comm_init on its single-device context. */
+#define RT1W_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+rt1w_status rt1w_context_create_multi(const int32_t *device_ids, int32_t n, rt1w_context **out);
+rt1w_status rt1w_comm_unique_id(uint8_t *out_id, size_t capacity);
+rt1w_status rt1w_context_comm_init(rt1w_context *ctx, const uint8_t *id, int32_t n_ranks, int32_t rank);
+/* rank and size of the context's communicator (0 and 1 outside one) and the devices it drives itself. */
+rt1w_status rt1w_context_get_comm(const rt1w_context *ctx, int32_t *rank, int32_t *n_ranks, int32_t *n_local_devices);
+/* The split rule: contiguous parts whose sizes differ by at most one (host code, no device needed). */
+void rt1w_shard_sample_range(int32_t rank, int32_t n_ranks, int32_t sample_begin, int32_t sample_end, int32_t *out_begin,
+                             int32_t *out_end);
 
 /* Lower + commit: walks the description, composes wrapper chains, expands
  * boxes, builds the SAH BVH (replaces `BVHNode::new`, bvh.rs:54-103) and

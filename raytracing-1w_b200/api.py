@@ -112,6 +112,7 @@ ABI_SYMBOLS = [
     "rt1w_abi_version", "rt1w_last_error", "rt1w_context_create", "rt1w_context_destroy", "rt1w_scene_create",
     "rt1w_scene_destroy", "rt1w_scene_get_info", "rt1w_scene_get_prims", "rt1w_lower_prims", "rt1w_lower_face_groups", "rt1w_render",
     "rt1w_render_device", "rt1w_render_rgb8", "rt1w_trace_closest", "rt1w_resolve_rgb8", "rt1w_philox4x32",
+    "rt1w_context_create_multi", "rt1w_comm_unique_id", "rt1w_context_comm_init", "rt1w_context_get_comm", "rt1w_shard_sample_range",
     "rt1w_eval_light_pdf", "rt1w_eval_texture", "rt1w_eval_perlin", "rt1w_eval_dielectric", "rt1w_eval_scatter",
 ]
 
@@ -155,6 +156,12 @@ def load_library():
     lib.rt1w_resolve_rgb8.restype = None
     lib.rt1w_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rt1w_philox4x32.restype = None
+    lib.rt1w_context_create_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(vp)]
+    lib.rt1w_comm_unique_id.argtypes = [vp, C.c_size_t]
+    lib.rt1w_context_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    lib.rt1w_context_get_comm.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.rt1w_shard_sample_range.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 2
+    lib.rt1w_shard_sample_range.restype = None
     lib.rt1w_eval_light_pdf.argtypes = [vp, C.c_int32, vp, vp, C.c_size_t, vp]
     lib.rt1w_eval_texture.argtypes = [vp, C.c_int32, vp, vp, C.c_size_t, vp]
     lib.rt1w_eval_perlin.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_size_t, vp]
@@ -435,11 +442,46 @@ def lower_face_groups(desc):
 
 
 # --------------------------------------------------------------------------- device objects
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rt1w_comm_unique_id: the id rank 0 makes and the host side ships to the other ranks (one process per GPU)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(load_library().rt1w_comm_unique_id(buf, COMM_ID_BYTES))
+    return bytes(buf)
+
+
+def shard_sample_range(rank, n_ranks, sample_begin, sample_end):
+    """rt1w_shard_sample_range: the library's split rule (host code)."""
+    b, e = C.c_int32(), C.c_int32()
+    load_library().rt1w_shard_sample_range(rank, n_ranks, sample_begin, sample_end, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
 class Context:
+    """rt1w_context_create (one device) or, given a list of device ids, rt1w_context_create_multi (one process driving
+    several GPUs: sample ranges sharded inside the library, NCCL reduce to the first device)."""
+
     def __init__(self, device_id=0):
         lib = load_library()
         self._h = C.c_void_p()
-        _check(lib.rt1w_context_create(device_id, C.byref(self._h)))
+        if isinstance(device_id, (list, tuple)):
+            ids = (C.c_int32 * len(device_id))(*device_id)
+            _check(lib.rt1w_context_create_multi(ids, len(device_id), C.byref(self._h)))
+        else:
+            _check(lib.rt1w_context_create(device_id, C.byref(self._h)))
+
+    def comm_init(self, unique_id, n_ranks, rank):
+        """rt1w_context_comm_init: joins the communicator of a one-process-per-GPU job; render calls become collective."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _check(load_library().rt1w_context_comm_init(self._h, buf, n_ranks, rank))
+
+    def comm(self):
+        """-> (rank, ranks, devices this context drives itself)."""
+        r, n, d = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(load_library().rt1w_context_get_comm(self._h, C.byref(r), C.byref(n), C.byref(d)))
+        return r.value, n.value, d.value
 
     def eval_dielectric(self, unit_dir, normal, ratio):
         """Device `reflect`, `refract`, `reflectance` (material.rs:94-96,114-125) for n unit directions / normals / index ratios."""
@@ -499,7 +541,7 @@ class Scene:
     def render_into(self, camera, params, out, stat=None):
         """rt1w_render into caller-provided (e.g. pinned) host arrays."""
         st = RenderStats()
-        _check(load_library().rt1w_render(self._h, C.byref(camera), C.byref(params), C.c_void_p(out.ctypes.data),
+        _check(load_library().rt1w_render(self._h, C.byref(camera), C.byref(params), C.c_void_p(out.ctypes.data) if out is not None else None,
                                           C.c_void_p(stat.ctypes.data) if stat is not None else None, C.byref(st)))
         return st
 

@@ -9,12 +9,14 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rt1w.h"
 #include "bvh.h"
 #include "lbvh.h"
 #include "lower.h"
+#include "nccl_dl.h"
 #include "render.h"
 
 using namespace rt1w;
@@ -171,6 +173,11 @@ struct rt1w_context {
     uint8_t *d_rgb8 = nullptr;
     size_t accum_pixels = 0, stat_pixels = 0, rgb8_pixels = 0;
     std::mutex lock; // calls on one context are serialised (rt1w.h "Threading")
+    // Multi-GPU: a context that belongs to a communicator renders ITS share of the sample range of every
+    // render call and adds its radiance sums to rank 0's with one ncclReduce on the render stream.
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    std::vector<rt1w_context *> members; // rt1w_context_create_multi: the other devices' contexts (ranks 1..n-1), owned by this one
 };
 
 struct rt1w_scene {
@@ -194,10 +201,12 @@ struct rt1w_scene {
     DLight *d_lights = nullptr;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> tex_objects;
+    std::vector<rt1w_scene *> replicas; // multi-device context: the same scene committed on ranks 1..n-1
 };
 
 static void scene_release(rt1w_scene *s) {
     if (!s) return;
+    for (rt1w_scene *r : s->replicas) scene_release(r);
     if (s->ctx) cudaSetDevice(s->ctx->device);
     for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
     for (auto a : s->arrays) cudaFreeArray(a);
@@ -212,8 +221,7 @@ int32_t rt1w_abi_version(void) { return RT1W_ABI_VERSION; }
 
 const char *rt1w_last_error(void) { return g_error.c_str(); }
 
-rt1w_status rt1w_context_create(int32_t device_id, rt1w_context **out) {
-    if (!out) return fail(RT1W_ERR_INVALID, "null output pointer");
+static rt1w_status context_create_impl(int32_t device_id, rt1w_context **out) {
     *out = nullptr;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -237,10 +245,109 @@ rt1w_status rt1w_context_create(int32_t device_id, rt1w_context **out) {
     return RT1W_OK;
 }
 
+rt1w_status rt1w_context_create(int32_t device_id, rt1w_context **out) {
+    if (!out) return fail(RT1W_ERR_INVALID, "null output pointer");
+    return context_create_impl(device_id, out);
+}
+
+static rt1w_status fail_nccl(const char *what, ncclResult_t r) {
+    const NcclApi &nccl = nccl_api();
+    g_error = std::string(what) + ": " + (nccl.GetErrorString ? nccl.GetErrorString(r) : "NCCL error");
+    return RT1W_ERR_CUDA;
+}
+
+rt1w_status rt1w_context_create_multi(const int32_t *device_ids, int32_t n, rt1w_context **out) {
+    if (!out || !device_ids || n <= 0) return fail(RT1W_ERR_INVALID, "null output pointer or empty device list");
+    *out = nullptr;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return fail(RT1W_ERR_INVALID, "a device may appear only once in the device list");
+    std::vector<rt1w_context *> all(size_t(n), nullptr);
+    auto destroy_all = [&] {
+        for (rt1w_context *c : all)
+            if (c) c->members.clear(), rt1w_context_destroy(c);
+    };
+    for (int i = 0; i < n; ++i) {
+        rt1w_status st = context_create_impl(device_ids[i], &all[i]);
+        if (st != RT1W_OK) {
+            destroy_all();
+            return st;
+        }
+    }
+    if (n > 1) {
+        const NcclApi &nccl = nccl_api();
+        if (!nccl.error.empty()) {
+            destroy_all();
+            return fail(RT1W_ERR_UNSUPPORTED, nccl.error);
+        }
+        std::vector<ncclComm_t> comms(size_t(n), nullptr);
+        std::vector<int> devs(device_ids, device_ids + n);
+        ncclResult_t r = nccl.CommInitAll(comms.data(), n, devs.data());
+        if (r != ncclSuccess) {
+            destroy_all();
+            return fail_nccl("ncclCommInitAll", r);
+        }
+        for (int i = 0; i < n; ++i) all[i]->comm = comms[i], all[i]->comm_rank = i, all[i]->comm_size = n;
+    }
+    all[0]->members.assign(all.begin() + 1, all.end());
+    *out = all[0];
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_comm_unique_id(uint8_t *out_id, size_t capacity) {
+    if (!out_id || capacity < RT1W_COMM_ID_BYTES) return fail(RT1W_ERR_INVALID, "the id buffer must hold RT1W_COMM_ID_BYTES bytes");
+    static_assert(RT1W_COMM_ID_BYTES == sizeof(ncclUniqueId), "rt1w.h must reserve an ncclUniqueId");
+    const NcclApi &nccl = nccl_api();
+    if (!nccl.error.empty()) return fail(RT1W_ERR_UNSUPPORTED, nccl.error);
+    ncclUniqueId id;
+    ncclResult_t r = nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail_nccl("ncclGetUniqueId", r);
+    std::memcpy(out_id, &id, sizeof(id));
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_context_comm_init(rt1w_context *ctx, const uint8_t *id, int32_t n_ranks, int32_t rank) {
+    if (!ctx || !id || n_ranks <= 0 || rank < 0 || rank >= n_ranks) return fail(RT1W_ERR_INVALID, "bad communicator arguments");
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    if (ctx->comm || !ctx->members.empty()) return fail(RT1W_ERR_STATE, "the context already belongs to a communicator");
+    if (n_ranks == 1) return RT1W_OK;
+    const NcclApi &nccl = nccl_api();
+    if (!nccl.error.empty()) return fail(RT1W_ERR_UNSUPPORTED, nccl.error);
+    RT1W_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = nccl.CommInitRank(&comm, n_ranks, uid, rank);
+    if (r != ncclSuccess) return fail_nccl("ncclCommInitRank", r);
+    ctx->comm = comm, ctx->comm_rank = rank, ctx->comm_size = n_ranks;
+    return RT1W_OK;
+}
+
+rt1w_status rt1w_context_get_comm(const rt1w_context *ctx, int32_t *rank, int32_t *n_ranks, int32_t *n_local_devices) {
+    if (!ctx) return fail(RT1W_ERR_INVALID, "null context");
+    if (rank) *rank = ctx->comm_rank;
+    if (n_ranks) *n_ranks = ctx->comm_size;
+    if (n_local_devices) *n_local_devices = int32_t(1 + ctx->members.size());
+    return RT1W_OK;
+}
+
+void rt1w_shard_sample_range(int32_t rank, int32_t n_ranks, int32_t sample_begin, int32_t sample_end, int32_t *out_begin, int32_t *out_end) {
+    // contiguous ranges whose sizes differ by at most one; the Philox counter carries the GLOBAL sample index, so the image
+    // does not depend on the split (up to the order of the fp32 additions)
+    const int64_t total = sample_end > sample_begin ? int64_t(sample_end) - sample_begin : 0;
+    const int64_t base = n_ranks > 0 ? total / n_ranks : total, extra = n_ranks > 0 ? total % n_ranks : 0;
+    const int64_t b = int64_t(rank) * base + std::min<int64_t>(rank, extra);
+    if (out_begin) *out_begin = int32_t(sample_begin + b);
+    if (out_end) *out_end = int32_t(sample_begin + b + base + (rank < extra ? 1 : 0));
+}
+
 void rt1w_context_destroy(rt1w_context *ctx) {
     if (!ctx) return;
+    for (rt1w_context *m : ctx->members) rt1w_context_destroy(m);
+    ctx->members.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
     pool_free(ctx->pool);
     cudaFree(ctx->d_accum), cudaFree(ctx->d_stat), cudaFree(ctx->d_rgb8);
     cudaFreeHost(ctx->h_ctr);
@@ -278,10 +385,8 @@ rt1w_status rt1w_lower_face_groups(const rt1w_scene_desc *desc, int32_t *group_o
     return RT1W_OK;
 }
 
-rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt1w_scene **out) {
-    if (!ctx || !out) return fail(RT1W_ERR_INVALID, "null context or output pointer");
+static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *desc, rt1w_scene **out) {
     *out = nullptr;
-    std::lock_guard<std::mutex> guard(ctx->lock);
     const auto t0 = std::chrono::steady_clock::now();
     LoweredScene low;
     std::string err;
@@ -513,6 +618,35 @@ rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt
     return RT1W_OK;
 }
 
+rt1w_status rt1w_scene_create(rt1w_context *ctx, const rt1w_scene_desc *desc, rt1w_scene **out) {
+    if (!ctx || !out) return fail(RT1W_ERR_INVALID, "null context or output pointer");
+    *out = nullptr;
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    if (ctx->members.empty()) return scene_create_impl(ctx, desc, out);
+    // a multi-device context: the scene is replicated, every device commits its own copy, all at once
+    const size_t n = 1 + ctx->members.size();
+    std::vector<rt1w_scene *> made(n, nullptr);
+    std::vector<rt1w_status> status(n, RT1W_OK);
+    std::vector<std::string> message(n);
+    std::vector<std::thread> workers;
+    for (size_t i = 1; i < n; ++i)
+        workers.emplace_back([&, i] {
+            status[i] = scene_create_impl(ctx->members[i - 1], desc, &made[i]);
+            if (status[i] != RT1W_OK) message[i] = g_error;
+        });
+    status[0] = scene_create_impl(ctx, desc, &made[0]);
+    if (status[0] != RT1W_OK) message[0] = g_error;
+    for (auto &w : workers) w.join();
+    for (size_t i = 0; i < n; ++i)
+        if (status[i] != RT1W_OK) {
+            for (rt1w_scene *m : made) scene_release(m);
+            return fail(status[i], message[i]);
+        }
+    made[0]->replicas.assign(made.begin() + 1, made.end());
+    *out = made[0];
+    return RT1W_OK;
+}
+
 void rt1w_scene_destroy(rt1w_scene *scene) { scene_release(scene); }
 
 rt1w_status rt1w_scene_get_info(const rt1w_scene *scene, rt1w_scene_info *out) {
@@ -529,19 +663,45 @@ rt1w_status rt1w_scene_get_prims(const rt1w_scene *scene, rt1w_flat_prim *out, i
     return RT1W_OK;
 }
 
+static rt1w_status ensure_buffers(rt1w_context *ctx, size_t pixels, bool stat, bool rgb8) {
+    if (ctx->accum_pixels < pixels) {
+        cudaFree(ctx->d_accum), ctx->d_accum = nullptr, ctx->accum_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_accum), sizeof(float) * 3 * pixels));
+        ctx->accum_pixels = pixels;
+    }
+    if (stat && ctx->stat_pixels < pixels) {
+        cudaFree(ctx->d_stat), ctx->d_stat = nullptr, ctx->stat_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_stat), sizeof(float) * 6 * pixels));
+        ctx->stat_pixels = pixels;
+    }
+    if (rgb8 && ctx->rgb8_pixels < pixels) {
+        cudaFree(ctx->d_rgb8), ctx->d_rgb8 = nullptr, ctx->rgb8_pixels = 0;
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rgb8), 3 * pixels));
+        ctx->rgb8_pixels = pixels;
+    }
+    return RT1W_OK;
+}
+
+// One device's part of a render call: its share of the sample range (all of it outside a communicator), then - inside a
+// communicator - the one exchange step of the path, ncclReduce(sum, fp32) of the radiance sums to rank 0 on the render
+// stream.  d_accum / d_stat: this device's buffers; after the call rank 0's hold the whole image.
 static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *d_accum, float *d_stat,
                                  cudaStream_t stream, rt1w_render_stats *stats) {
     rt1w_context *ctx = scene->ctx;
-    const rt1w_render_params &p = *params;
+    rt1w_render_params p = *params;
     if (p.width <= 0 || p.height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
     if (p.sample_end <= p.sample_begin || p.sample_begin < 0) return fail(RT1W_ERR_INVALID, "empty sample range");
     if (p.sample_end - p.sample_begin >= (1 << 24)) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^24-1 samples per pixel in one call");
     if (p.max_depth < 0 || p.max_depth > 255) return fail(RT1W_ERR_UNSUPPORTED, "max_depth must be in [0, 255]");
     if (uint64_t(p.width) * uint64_t(p.height) >= (1ull << 31)) return fail(RT1W_ERR_UNSUPPORTED, "image too large");
-    const uint64_t all_paths = uint64_t(p.width) * uint64_t(p.height) * uint64_t(p.sample_end - p.sample_begin);
     if (p.pool_paths > (1 << 30)) return fail(RT1W_ERR_UNSUPPORTED, "pool_paths must not exceed 2^30");
+    const bool sharded = ctx->comm != nullptr && ctx->comm_size > 1;
+    if (sharded) rt1w_shard_sample_range(ctx->comm_rank, ctx->comm_size, params->sample_begin, params->sample_end, &p.sample_begin, &p.sample_end);
+    const int32_t my_samples = p.sample_end - p.sample_begin; // 0: more ranks than samples - this one only joins the reduce
+    const uint64_t all_paths = uint64_t(p.width) * uint64_t(p.height) * uint64_t(my_samples);
     uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
     if (p.pool_paths <= 0 && all_paths < want_pool) want_pool = uint32_t((all_paths + 1023u) & ~uint64_t(1023u)); // small renders: one wave holds every path
+    if (want_pool == 0) want_pool = 1024;
     if (ctx->pool.allocated < want_pool || (ctx->pool.material_mask & scene->material_mask) != scene->material_mask) {
         const uint32_t grow = ctx->pool.allocated > want_pool ? ctx->pool.allocated : want_pool;
         cudaError_t e = pool_alloc(ctx->pool, grow, scene->material_mask | ctx->pool.material_mask);
@@ -552,7 +712,7 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     args.pool = ctx->pool;
     args.pool.capacity = want_pool;
     DRenderParams &rp = args.rp;
-    rp.width = p.width, rp.height = p.height, rp.sample_begin = p.sample_begin, rp.n_samples = p.sample_end - p.sample_begin;
+    rp.width = p.width, rp.height = p.height, rp.sample_begin = p.sample_begin, rp.n_samples = my_samples;
     rp.max_depth = p.max_depth, rp.flags = p.flags, rp.seed_lo = uint32_t(p.seed), rp.seed_hi = uint32_t(p.seed >> 32);
     for (int k = 0; k < 3; ++k) rp.background[k] = float(p.background[k]);
     rp.stat_clamp = p.stat_clamp > 0.0 ? float(p.stat_clamp) : INFINITY;
@@ -561,7 +721,7 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     rp.pool = int32_t(want_pool);
     rp.tile_shift = 16; // 65536 pixels = 768 KB of sums per tile; fewer when the sample count is huge (tile_paths <= 2^30)
     while (rp.tile_shift > 5 && (uint64_t(rp.n_samples) << rp.tile_shift) > (1ull << 30)) --rp.tile_shift;
-    rp.tile_paths = uint32_t(rp.n_samples) << rp.tile_shift;
+    rp.tile_paths = uint32_t(std::max(rp.n_samples, 1)) << rp.tile_shift;
     rp.inv_w1 = 1.0 / double(p.width - 1), rp.inv_h1 = 1.0 / double(p.height - 1); // a 1-pixel axis: inf, as the reference's division by zero
     rp.inv_width_up = (1.0 / double(p.width)) * (1.0 + 0x1p-50), rp.inv_tile_paths_up = (1.0 / double(rp.tile_paths)) * (1.0 + 0x1p-50);
     DCamera &c = args.cam;
@@ -576,14 +736,20 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     args.accum = d_accum;
     args.stat = d_stat;
 
+    RT1W_CUDA(cudaEventRecord(ctx->ev0, stream));
     RT1W_CUDA(cudaMemsetAsync(d_accum, 0, sizeof(float) * 3 * size_t(rp.n_pixels), stream));
     if (d_stat) RT1W_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(float) * 6 * size_t(rp.n_pixels), stream));
-    RT1W_CUDA(cudaEventRecord(ctx->ev0, stream));
     WaveStats ws;
     ws.profile = (p.flags & RT1W_FLAG_PROFILE) != 0;
     if (rp.total_paths > 0) {
         cudaError_t e = render_waves(args, scene->material_mask, ctx->h_ctr, stream, ctx->sm_count, ws);
         if (e != cudaSuccess) return fail_cuda("wavefront render", e);
+    }
+    if (sharded) { // in place: rank 0 receives where it sent
+        const NcclApi &nccl = nccl_api();
+        ncclResult_t r = nccl.Reduce(d_accum, d_accum, 3 * size_t(rp.n_pixels), ncclFloat, ncclSum, 0, ctx->comm, stream);
+        if (r == ncclSuccess && d_stat) r = nccl.Reduce(d_stat, d_stat, 6 * size_t(rp.n_pixels), ncclFloat, ncclSum, 0, ctx->comm, stream);
+        if (r != ncclSuccess) return fail_nccl("ncclReduce of the radiance sums", r);
     }
     RT1W_CUDA(cudaEventRecord(ctx->ev1, stream));
     RT1W_CUDA(cudaStreamSynchronize(stream));
@@ -600,58 +766,97 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     return RT1W_OK;
 }
 
+// A render call on a multi-device context (rt1w_context_create_multi): one host thread per device, each running
+// render_common on its replica of the scene; the reduce inside leaves the image in rank 0's buffers (d_accum / d_stat on
+// the first device, stream = its render stream).  stats: paths, rays and launches summed, waves and time the maximum.
+static rt1w_status render_dispatch(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *d_accum, float *d_stat,
+                                   cudaStream_t stream, rt1w_render_stats *stats) {
+    rt1w_context *ctx = scene->ctx;
+    if (ctx->members.empty()) return render_common(scene, camera, params, d_accum, d_stat, stream, stats);
+    const size_t n = 1 + ctx->members.size();
+    if (scene->replicas.size() + 1 != n) return fail(RT1W_ERR_STATE, "the scene was not committed on this multi-device context");
+    const size_t pixels = params->width > 0 && params->height > 0 ? size_t(params->width) * size_t(params->height) : 0;
+    std::vector<rt1w_status> status(n, RT1W_OK);
+    std::vector<std::string> message(n);
+    std::vector<rt1w_render_stats> st(n);
+    auto run = [&](size_t i) {
+        rt1w_context *c = i == 0 ? ctx : ctx->members[i - 1];
+        rt1w_scene *sc = i == 0 ? scene : scene->replicas[i - 1];
+        if (cudaSetDevice(c->device) != cudaSuccess) {
+            status[i] = RT1W_ERR_CUDA, message[i] = "cudaSetDevice failed";
+            return;
+        }
+        float *acc = d_accum, *stt = d_stat;
+        cudaStream_t str = stream;
+        if (i > 0) {
+            status[i] = ensure_buffers(c, pixels, d_stat != nullptr, false);
+            acc = c->d_accum, stt = d_stat ? c->d_stat : nullptr, str = c->stream;
+        }
+        if (status[i] == RT1W_OK) status[i] = render_common(sc, camera, params, acc, stt, str, &st[i]);
+        if (status[i] != RT1W_OK) message[i] = g_error;
+    };
+    std::vector<std::thread> workers;
+    for (size_t i = 1; i < n; ++i) workers.emplace_back(run, i);
+    run(0);
+    for (auto &w : workers) w.join();
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < n; ++i)
+        if (status[i] != RT1W_OK) return fail(status[i], "device " + std::to_string(i) + ": " + message[i]);
+    if (stats) {
+        *stats = st[0];
+        for (size_t i = 1; i < n; ++i) {
+            stats->paths += st[i].paths, stats->rays += st[i].rays, stats->launches += st[i].launches;
+            stats->waves = std::max(stats->waves, st[i].waves), stats->render_ms = std::max(stats->render_ms, st[i].render_ms);
+            for (int k = 0; k < K_COUNT; ++k) stats->kernel_ms[k] += st[i].kernel_ms[k], stats->kernel_launches[k] += st[i].kernel_launches[k];
+        }
+    }
+    return RT1W_OK;
+}
+
 rt1w_status rt1w_render(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *out_rgb_sum, float *out_stat,
                         rt1w_render_stats *stats) {
-    if (!scene || !camera || !params || !out_rgb_sum) return fail(RT1W_ERR_INVALID, "null argument");
+    if (!scene || !camera || !params) return fail(RT1W_ERR_INVALID, "null argument");
     rt1w_context *ctx = scene->ctx;
+    const bool root = ctx->comm_rank == 0; // only rank 0 of a communicator receives the image
+    if (root && !out_rgb_sum) return fail(RT1W_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> guard(ctx->lock);
     RT1W_CUDA(cudaSetDevice(ctx->device));
     if (params->width <= 0 || params->height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
     const size_t pixels = size_t(params->width) * size_t(params->height);
-    const bool want_stat = out_stat != nullptr;
-    if (want_stat && !(params->flags & RT1W_FLAG_STATS)) return fail(RT1W_ERR_INVALID, "out_stat needs RT1W_FLAG_STATS");
-    if (ctx->accum_pixels < pixels) {
-        cudaFree(ctx->d_accum), ctx->d_accum = nullptr, ctx->accum_pixels = 0;
-        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_accum), sizeof(float) * 3 * pixels));
-        ctx->accum_pixels = pixels;
-    }
-    if (want_stat && ctx->stat_pixels < pixels) {
-        cudaFree(ctx->d_stat), ctx->d_stat = nullptr, ctx->stat_pixels = 0;
-        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_stat), sizeof(float) * 6 * pixels));
-        ctx->stat_pixels = pixels;
-    }
-    rt1w_status st = render_common(scene, camera, params, ctx->d_accum, want_stat ? ctx->d_stat : nullptr, ctx->stream, stats);
+    const bool want_stat = (params->flags & RT1W_FLAG_STATS) != 0 && (out_stat != nullptr || !root);
+    if (out_stat && !(params->flags & RT1W_FLAG_STATS)) return fail(RT1W_ERR_INVALID, "out_stat needs RT1W_FLAG_STATS");
+    rt1w_status st = ensure_buffers(ctx, pixels, want_stat, false);
     if (st != RT1W_OK) return st;
-    RT1W_CUDA(cudaMemcpyAsync(out_rgb_sum, ctx->d_accum, sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
-    if (want_stat) RT1W_CUDA(cudaMemcpyAsync(out_stat, ctx->d_stat, sizeof(float) * 6 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
-    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    st = render_dispatch(scene, camera, params, ctx->d_accum, want_stat ? ctx->d_stat : nullptr, ctx->stream, stats);
+    if (st != RT1W_OK) return st;
+    if (root) {
+        RT1W_CUDA(cudaMemcpyAsync(out_rgb_sum, ctx->d_accum, sizeof(float) * 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_stat && out_stat) RT1W_CUDA(cudaMemcpyAsync(out_stat, ctx->d_stat, sizeof(float) * 6 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
+        RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     return RT1W_OK;
 }
 
 rt1w_status rt1w_render_rgb8(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, uint8_t *out_rgb8,
                              rt1w_render_stats *stats) {
-    if (!scene || !camera || !params || !out_rgb8) return fail(RT1W_ERR_INVALID, "null argument");
+    if (!scene || !camera || !params) return fail(RT1W_ERR_INVALID, "null argument");
     rt1w_context *ctx = scene->ctx;
+    const bool root = ctx->comm_rank == 0;
+    if (root && !out_rgb8) return fail(RT1W_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> guard(ctx->lock);
     RT1W_CUDA(cudaSetDevice(ctx->device));
     if (params->width <= 0 || params->height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
     if (params->flags & RT1W_FLAG_STATS) return fail(RT1W_ERR_INVALID, "RT1W_FLAG_STATS is only available through rt1w_render");
     const size_t pixels = size_t(params->width) * size_t(params->height);
-    if (ctx->accum_pixels < pixels) {
-        cudaFree(ctx->d_accum), ctx->d_accum = nullptr, ctx->accum_pixels = 0;
-        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_accum), sizeof(float) * 3 * pixels));
-        ctx->accum_pixels = pixels;
-    }
-    if (ctx->rgb8_pixels < pixels) {
-        cudaFree(ctx->d_rgb8), ctx->d_rgb8 = nullptr, ctx->rgb8_pixels = 0;
-        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rgb8), 3 * pixels));
-        ctx->rgb8_pixels = pixels;
-    }
-    rt1w_status st = render_common(scene, camera, params, ctx->d_accum, nullptr, ctx->stream, stats);
+    rt1w_status st = ensure_buffers(ctx, pixels, false, root);
     if (st != RT1W_OK) return st;
-    RT1W_CUDA(resolve_launch(ctx->d_accum, 3 * pixels, params->sample_end - params->sample_begin, ctx->d_rgb8, ctx->stream));
-    RT1W_CUDA(cudaMemcpyAsync(out_rgb8, ctx->d_rgb8, 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
-    RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    st = render_dispatch(scene, camera, params, ctx->d_accum, nullptr, ctx->stream, stats);
+    if (st != RT1W_OK) return st;
+    if (root) { // the mean divides by the WHOLE sample range: the reduce has added every rank's share
+        RT1W_CUDA(resolve_launch(ctx->d_accum, 3 * pixels, params->sample_end - params->sample_begin, ctx->d_rgb8, ctx->stream));
+        RT1W_CUDA(cudaMemcpyAsync(out_rgb8, ctx->d_rgb8, 3 * pixels, cudaMemcpyDeviceToHost, ctx->stream));
+        RT1W_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     return RT1W_OK;
 }
 
@@ -662,7 +867,7 @@ rt1w_status rt1w_render_device(rt1w_scene *scene, const rt1w_camera *camera, con
     std::lock_guard<std::mutex> guard(ctx->lock);
     RT1W_CUDA(cudaSetDevice(ctx->device));
     if (params->flags & RT1W_FLAG_STATS) return fail(RT1W_ERR_INVALID, "RT1W_FLAG_STATS is only available through rt1w_render");
-    return render_common(scene, camera, params, d_rgb_sum, nullptr, static_cast<cudaStream_t>(cuda_stream), stats);
+    return render_dispatch(scene, camera, params, d_rgb_sum, nullptr, static_cast<cudaStream_t>(cuda_stream), stats);
 }
 
 rt1w_status rt1w_trace_closest(rt1w_scene *scene, const rt1w_ray *rays, size_t n, uint64_t seed, int32_t *prim_id, float *t, float *normal3,

@@ -1,12 +1,14 @@
 // main.cpp — the reference's `main` (main.rs:797-1010) on top of the C ABI.
 //
-//   rt1w_main [scene] [--width W] [--spp N] [--depth D] [--seed S] [--earth earthmap.ppm] [--device K] > image.ppm
+//   rt1w_main [scene] [--width W] [--spp N] [--depth D] [--seed S] [--earth earthmap.ppm] [--device K | --gpus N] > image.ppm
 //
 // `scene` is an arm of `match 5 { .. }` (main.rs:815-937) by number (0..7) or name (random_scene, two_spheres,
 // two_perlin_spheres, earth, simple_light, cornel_box, cornel_smoke, final_scene); default 5 like the reference.
 // Everything up to the pixel loop is the reference's code path in the C++ mirror (scene function, per-arm
 // settings, Camera::new); the pixel loop (main.rs:957-1001) is one rt1w_render_rgb8 call per progress chunk of
 // the sample range; the P3 text goes to stdout and the progress line to stderr as in main.rs:953,995-1009.
+// `--gpus N`: devices 0..N-1 render every chunk together (rt1w_context_create_multi: sample ranges sharded inside the
+// library, one ncclReduce of the radiance sums per chunk); the call sequence below stays the same.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,7 +46,7 @@ int fail(const char *what) {
 
 int main(int argc, char **argv) {
     int which = 5; // `match 5` (main.rs:815)
-    int width = 0, spp = 0, depth = 0, device = 0;
+    int width = 0, spp = 0, depth = 0, device = 0, gpus = 1;
     uint64_t seed = 1;
     std::string earth_path = "assets/earthmap.ppm";
     for (int i = 1; i < argc; ++i) {
@@ -55,6 +57,7 @@ int main(int argc, char **argv) {
         else if (a == "--depth") depth = std::atoi(value());
         else if (a == "--seed") seed = std::strtoull(value(), nullptr, 10);
         else if (a == "--device") device = std::atoi(value());
+        else if (a == "--gpus") gpus = std::atoi(value());
         else if (a == "--earth") earth_path = value();
         else if (!a.empty() && (a[0] >= '0' && a[0] <= '9')) which = std::atoi(a.c_str());
         else which = rt1w::scene_id_from_name(a);
@@ -82,7 +85,13 @@ int main(int argc, char **argv) {
     const rt1w::Camera camera = setup->camera();
 
     rt1w_context *ctx = nullptr;
-    if (rt1w_context_create(device, &ctx) != RT1W_OK) return fail("rt1w_context_create");
+    if (gpus > 1) {
+        std::vector<int32_t> ids;
+        for (int g = 0; g < gpus; ++g) ids.push_back(device + g);
+        if (rt1w_context_create_multi(ids.data(), gpus, &ctx) != RT1W_OK) return fail("rt1w_context_create_multi");
+    } else if (rt1w_context_create(device, &ctx) != RT1W_OK) {
+        return fail("rt1w_context_create");
+    }
     rt1w_scene *scene = nullptr;
     if (rt1w_scene_create(ctx, &desc, &scene) != RT1W_OK) return fail("rt1w_scene_create");
 

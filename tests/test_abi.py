@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported(rt):
     assert set(names) == set(rt.api.ABI_SYMBOLS), "api.ABI_SYMBOLS out of date with include/rt1w.h"
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/rt1w.h but not exported by librt1w.so"
-    assert lib.rt1w_abi_version() == 1
+    assert lib.rt1w_abi_version() == 2
 
 
 def test_host_library_exports(rt):
@@ -88,3 +88,32 @@ def test_demo_driver_fails_loudly_without_a_gpu(rt):
     r = subprocess.run([exe, "cornel_box", "--width", "8", "--spp", "1"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "rt1w_context_create" in r.stderr
     assert not r.stdout.startswith("P3")
+
+
+def test_library_shard_rule_matches_the_host_side(rt):
+    """rt1w_shard_sample_range (what a communicator's ranks render) == shard.sample_range (host-side rule): a partition of
+    the sample range into contiguous parts whose sizes differ by at most one."""
+    import importlib
+
+    shard = importlib.import_module("raytracing-1w_b200.shard")
+    for world in (1, 2, 3, 4, 8):
+        for begin, end in ((0, 1), (0, 7), (0, 100), (0, 4096), (300, 400), (5, 6)):
+            ranges = [rt.api.shard_sample_range(r, world, begin, end) for r in range(world)]
+            assert ranges[0][0] == begin and ranges[-1][1] == end
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 0
+            assert [(a - begin, b - begin) for a, b in ranges] == [shard.sample_range(r, world, end - begin) for r in range(world)]
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_gpu(rt):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rt.api.Rt1wError) as e:
+        rt.api.Context([0, 1])
+    assert e.value.status == rt.api.ERR_NO_DEVICE
+    with pytest.raises(rt.api.Rt1wError) as e:
+        rt.api.Context([])
+    assert e.value.status == rt.api.ERR_INVALID

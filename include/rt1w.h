@@ -163,6 +163,9 @@ typedef struct rt1w_camera {
 /* BVH scenes: which wave kernel traverses (default: by BVH size).  Both return the same closest hits; parity tests force each. */
 #define RT1W_FLAG_BVH_LOCKSTEP 4u   /* a warp runs its 32 rays to the end together (short, even traversals) */
 #define RT1W_FLAG_BVH_PERSISTENT 8u /* lanes take a new ray as soon as theirs is done (long, uneven traversals) */
+/* BVH scenes: which tree is walked (default: by BVH size).  Same leaves, same conservative boxes, same closest hits. */
+#define RT1W_FLAG_BVH_BINARY 16u /* 32-byte nodes, two children per step */
+#define RT1W_FLAG_BVH_WIDE 32u   /* compressed 8-wide nodes (80 bytes, eight quantised child boxes per step) */
 
 /* kernel slots of rt1w_render_stats.kernel_ms / kernel_launches */
 #define RT1W_KERNEL_WAVE 0  /* k_wave / k_wave_bvh: scatter queued hits / start camera paths, closest hit, regroup per material */
@@ -199,9 +202,14 @@ typedef struct rt1w_scene_info {
     int32_t n_lights;
     int32_t bvh_depth;
     int32_t material_mask; /* bit m set when some primitive uses rt1w_material_type m */
-    double build_ms;       /* host lowering + SAH build */
+    double build_ms;       /* host lowering + BVH build (binary tree, then its collapse into the 8-wide tree) */
     double upload_ms;
     double sah_cost;
+    int32_t n_wide_nodes;  /* 80-byte nodes of the compressed 8-wide BVH (0: flat-scan scene) */
+    int32_t wide_depth;
+    int32_t wide_default;  /* 1: render and trace calls walk the 8-wide tree unless a flag says otherwise */
+    int32_t reserved;
+    double wide_children;  /* occupied slots per wide node */
 } rt1w_scene_info;
 
 /* One lowered primitive, in PRIMITIVE-ID order (DFS order of the description,

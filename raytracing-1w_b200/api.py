@@ -20,6 +20,8 @@ FLAG_STATS = 1
 FLAG_PROFILE = 2
 FLAG_BVH_LOCKSTEP = 4
 FLAG_BVH_PERSISTENT = 8
+FLAG_BVH_BINARY = 16
+FLAG_BVH_WIDE = 32
 
 SCENE_IDS = {"random_scene": 0, "two_spheres": 1, "two_perlin_spheres": 2, "earth": 3, "simple_light": 4,
              "cornel_box": 5, "cornel_smoke": 6, "final_scene": 7, "stress": 8, "one_weekend": 9}
@@ -84,7 +86,8 @@ class RenderStats(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [("n_prims", C.c_int32), ("n_bvh_nodes", C.c_int32), ("n_frames", C.c_int32), ("n_lights", C.c_int32),
                 ("bvh_depth", C.c_int32), ("material_mask", C.c_int32), ("build_ms", C.c_double),
-                ("upload_ms", C.c_double), ("sah_cost", C.c_double)]
+                ("upload_ms", C.c_double), ("sah_cost", C.c_double), ("n_wide_nodes", C.c_int32), ("wide_depth", C.c_int32),
+                ("wide_default", C.c_int32), ("reserved", C.c_int32), ("wide_children", C.c_double)]
 
 
 class FlatPrim(C.Structure):

@@ -18,8 +18,8 @@ OUT = os.path.join(PKG, "_build")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
 
-CUDA_SRCS = ["csrc/api.cu", "csrc/render.cu", "csrc/lbvh.cu", "csrc/lower.cpp", "csrc/bvh.cpp"]
-CUDA_HDRS = ["csrc/device_types.h", "csrc/kernels.cuh", "csrc/render.h", "csrc/lower.h", "csrc/bvh.h", "csrc/lbvh.h", "csrc/philox.h", "../include/rt1w.h"]
+CUDA_SRCS = ["csrc/api.cu", "csrc/render.cu", "csrc/lbvh.cu", "csrc/lower.cpp", "csrc/bvh.cpp", "csrc/bvh8.cpp"]
+CUDA_HDRS = ["csrc/device_types.h", "csrc/kernels.cuh", "csrc/render.h", "csrc/lower.h", "csrc/bvh.h", "csrc/bvh8.h", "csrc/nccl_dl.h", "csrc/lbvh.h", "csrc/philox.h", "../include/rt1w.h"]
 HOST_SRCS = ["host/scenes.cpp", "host/host_api.cpp"]
 HOST_HDRS = ["host/rt1w.hpp", "host/scenes.hpp", "host/host_api.h", "../include/rt1w.h"]
 

@@ -14,6 +14,7 @@
 
 #include "../../include/rt1w.h"
 #include "bvh.h"
+#include "bvh8.h"
 #include "lbvh.h"
 #include "lower.h"
 #include "nccl_dl.h"
@@ -42,6 +43,7 @@ rt1w_status fail_cuda(const char *what, cudaError_t e) {
 
 constexpr uint32_t kDefaultPool = 1u << 23; // rays in flight per wave: the queues stream through HBM, so bigger waves amortise launches and the tail
 constexpr int kLbvhFromPrims = 1 << 17;      // scenes from this many primitives on get their BVH built on the device
+constexpr int kWideFromNodes = 32768;        // BVHs from this many binary nodes on are walked through the compressed 8-wide tree by default
 constexpr int kMaxLeaf = 1; // single-primitive leaves: the f32 leaf-box test screens the f64 primitive solve
 
 // Bounds of a lowered primitive in its own frame (the box its wrapper chain rotates and translates).
@@ -182,6 +184,7 @@ struct rt1w_context {
 
 struct rt1w_scene {
     rt1w_context *ctx = nullptr;
+    int device = 0; // where the allocations below live (kept here: a scene may be released after its context)
     std::vector<rt1w_flat_prim> prims; // primitive-id order
     rt1w_scene_info info{};
     SceneView view{};
@@ -189,6 +192,7 @@ struct rt1w_scene {
     int n_textures = 0;
     // device allocations
     float4 *d_nodes = nullptr;
+    uint4 *d_wide_nodes = nullptr;
     DPrim *d_prims = nullptr;
     float4 *d_prim_boxes = nullptr;
     int32_t *d_prim_id = nullptr;
@@ -207,10 +211,10 @@ struct rt1w_scene {
 static void scene_release(rt1w_scene *s) {
     if (!s) return;
     for (rt1w_scene *r : s->replicas) scene_release(r);
-    if (s->ctx) cudaSetDevice(s->ctx->device);
+    cudaSetDevice(s->device);
     for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
     for (auto a : s->arrays) cudaFreeArray(a);
-    cudaFree(s->d_nodes), cudaFree(s->d_prims), cudaFree(s->d_prim_boxes), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
+    cudaFree(s->d_nodes), cudaFree(s->d_wide_nodes), cudaFree(s->d_prims), cudaFree(s->d_prim_boxes), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
     cudaFree(s->d_textures), cudaFree(s->d_perlins), cudaFree(s->d_images), cudaFree(s->d_image_dims), cudaFree(s->d_lights);
     delete s;
 }
@@ -464,6 +468,24 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
         ~NodeGuard() { cudaFree(p); }
     } node_guard{d_lbvh_nodes};
     if (bvh.depth > kStackSmem + kStackLocal - 2) return fail(RT1W_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+    // BVH scenes also get the compressed 8-wide tree (bvh8.h), collapsed from the binary one whichever builder made it.
+    // The leaves take the wide tree's order (a node's leaf slots are adjacent), the binary tree's leaf nodes are re-pointed:
+    // both trees index ONE primitive array and find the same closest hits.
+    Bvh8BuildResult wide;
+    if (!flat) {
+        if (d_lbvh_nodes) { // device-built: bring the nodes back (64 MB for a million primitives)
+            bvh.nodes.resize(n_bvh_nodes);
+            RT1W_CUDA(cudaMemcpy(bvh.nodes.data(), d_lbvh_nodes, sizeof(BvhNode32) * n_bvh_nodes, cudaMemcpyDeviceToHost));
+            cudaFree(d_lbvh_nodes), d_lbvh_nodes = nullptr;
+        }
+        collapse_to_bvh8(bvh.nodes.data(), bvh.nodes.size(), wide);
+        if (wide.leaf_remap.size() != n) return fail(RT1W_ERR_STATE, "wide BVH collapse lost primitives");
+        std::vector<uint32_t> new_of_old(n), order(n);
+        for (size_t i = 0; i < n; ++i) new_of_old[wide.leaf_remap[i]] = uint32_t(i), order[i] = bvh.prim_order[wide.leaf_remap[i]];
+        for (BvhNode32 &nd : bvh.nodes)
+            if (nd.count != 0) nd.left_first = new_of_old[nd.left_first];
+        bvh.prim_order.swap(order);
+    }
     std::vector<DPrim> dprims(n);
     std::vector<int32_t> prim_id(n);
     for (size_t i = 0; i < n; ++i) {
@@ -551,13 +573,18 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
 
     RT1W_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<rt1w_scene, void (*)(rt1w_scene *)> s(new rt1w_scene(), scene_release);
-    s->ctx = ctx;
+    s->ctx = ctx, s->device = ctx->device;
     static_assert(sizeof(BvhNode32) == 2 * sizeof(float4), "node layout");
     if (d_lbvh_nodes) {
         s->d_nodes = reinterpret_cast<float4 *>(d_lbvh_nodes), d_lbvh_nodes = nullptr;
     } else {
         RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
         RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
+    }
+    if (!wide.nodes.empty()) {
+        static_assert(sizeof(Bvh8Node) == 5 * sizeof(uint4), "wide node layout");
+        RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_wide_nodes), sizeof(Bvh8Node) * wide.nodes.size()));
+        RT1W_CUDA(cudaMemcpy(s->d_wide_nodes, wide.nodes.data(), sizeof(Bvh8Node) * wide.nodes.size(), cudaMemcpyHostToDevice));
     }
     RT1W_CUDA(upload(dprims, &s->d_prims));
     RT1W_CUDA(upload(prim_boxes, &s->d_prim_boxes));
@@ -603,6 +630,10 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     v.n_lights = int32_t(low.lights.size()), v.has_lights = low.has_lights ? 1 : 0;
     v.n_prims = int32_t(n), v.n_nodes = int32_t(n_bvh_nodes), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
     v.flat = flat ? 1 : 0;
+    v.wide_nodes = s->d_wide_nodes;
+    v.wide = !flat && n_bvh_nodes >= size_t(kWideFromNodes) ? 1 : 0;
+    if (const char *env = std::getenv("RT1W_BVH_LAYOUT")) // binary | wide: overrides the size rule (tuning, tests)
+        v.wide = !flat && std::strcmp(env, "wide") == 0 ? 1 : (std::strcmp(env, "binary") == 0 ? 0 : v.wide);
     v.rich_textures = 0;
     for (const DTexture &t : low.textures)
         if (t.type != RT1W_TEX_SOLID) v.rich_textures = 1;
@@ -614,6 +645,8 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     s->info.build_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     s->info.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     s->info.sah_cost = bvh.sah_cost;
+    s->info.n_wide_nodes = int32_t(wide.nodes.size()), s->info.wide_depth = wide.depth, s->info.wide_default = v.wide;
+    s->info.wide_children = wide.avg_children;
     *out = s.release();
     return RT1W_OK;
 }

@@ -34,6 +34,7 @@ constexpr int kStackLocal = 64 - RT1W_STACK_SMEM; // overflow entries (local mem
 
 struct SceneView {
     const float4 *nodes;       // 2 x float4 per node
+    const uint4 *wide_nodes;   // 5 x uint4 per node of the compressed 8-wide tree (bvh8.h), or nullptr
     const DPrim *prims;        // leaf order
     const float4 *prim_boxes;  // flat scenes: 3 x float4 per primitive in SCAN order (see flat_stage), else nullptr
     const int32_t *prim_id;    // leaf index -> primitive id (DFS order of the description)
@@ -47,6 +48,7 @@ struct SceneView {
     int32_t n_lights, has_lights;
     int32_t n_prims, n_nodes, n_perlins, n_frames;
     int32_t flat; // scan the primitive list (closest_hit_flat) instead of walking the BVH
+    int32_t wide; // BVH scenes: walk the 8-wide tree by default (render flags may force either layout)
     int32_t rich_textures; // some texture is not a SolidColor
 };
 
@@ -381,6 +383,8 @@ RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, Trav &T) {
 
 RT1W_DEV bool trav_interior(const Trav &T) { return (T.ref >> 29) == 0u; }
 RT1W_DEV bool trav_done(const Trav &T) { return T.ref == kTravDone; }
+RT1W_DEV bool trav_at_leaf(const Trav &T) { return !trav_interior(T) && !trav_done(T); }
+RT1W_DEV void trav_reset(Trav &T) { T.ref = kTravDone, T.sp = 0; }
 
 RT1W_DEV void trav_pop(Trav &T, const uint2 *stack, int stride, const uint2 *overflow) { // next stacked subtree that can still hold a closer hit
     // (taking one entry per step instead of looping here was measured slower: 479 vs 507 Mrays/s on the 1 M-sphere scene)
@@ -449,6 +453,142 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
     while (!trav_done(T)) {
         while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, overflow);
         if (!trav_done(T)) trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, overflow);
+    }
+    t_best = T.best, leaf_best = T.best_leaf;
+    return T.best_leaf >= 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// extend: closest hit over the compressed 8-wide BVH (bvh8.h; replaces BVHNode::hit, bvh.rs:25-50, for big scenes)
+// ------------------------------------------------------------------------------------------
+// One step = ONE 80-byte node fetch and eight child tests.  Child boxes are bytes on the node's power-of-two grid, so a
+// plane distance is t = q * (step / d) + (origin - o) / d: one int-to-float conversion and one FMA per plane, on the
+// SlabRay terms of the binary traversal (same FMA form, same rounding, covered by the same box padding); the near and far
+// byte of every axis is picked once per node from the sign of the direction instead of a min / max per child.
+// The hit slots are kept as a bit mask in TRAVERSAL-PRIORITY order (bit slot ^ octant, bvh8.h): the highest set bit is the
+// next child, and what is left of a node's mask is its single stack entry.  Leaf slots (one primitive each) are solved in
+// f64 as soon as the node has been tested - before any of its interior children is entered - so the nearest hits shrink
+// the ray early.  No entry distances are stored: a stacked child the best hit has meanwhile beaten is culled when its node
+// is fetched (all of its children miss), as in Ylitie et al.
+struct TravW {
+    SlabRay s;
+    double best;   // closest accepted root so far
+    float bestf;   // its f32 upper bound, for the node tests
+    int best_leaf; // leaf | side << kLeafBits, or -1
+    uint2 ng;      // interior children still to visit: x = child_base, y = pending slots (bits 8..15, priority order) | imask (bits 0..7)
+    uint2 lg;      // leaf slots the last node test hit: x = prim_base, y = pending slots (bits 8..15, priority order) | leaf_mask
+    uint32_t oct;  // bit k set: direction component k >= 0
+    int sp;
+};
+
+// 8-bit slot mask -> priority order: bit (s ^ oct) of the result = bit s of m
+RT1W_DEV uint32_t octant_order(uint32_t m, uint32_t oct) {
+    if (oct & 1u) m = ((m & 0xaau) >> 1) | ((m & 0x55u) << 1);
+    if (oct & 2u) m = ((m & 0xccu) >> 2) | ((m & 0x33u) << 2);
+    if (oct & 4u) m = ((m & 0xf0u) >> 4) | ((m & 0x0fu) << 4);
+    return m;
+}
+
+RT1W_DEV void trav_reset(TravW &T) { T.ng = make_uint2(0u, 0u), T.lg = make_uint2(0u, 0u), T.sp = 0; }
+RT1W_DEV bool trav_at_leaf(const TravW &T) { return (T.lg.y >> 8) != 0u; }
+RT1W_DEV bool trav_interior(const TravW &T) { return (T.lg.y >> 8) == 0u && ((T.ng.y >> 8) != 0u || T.sp > 0); }
+RT1W_DEV bool trav_done(const TravW &T) { return (T.lg.y >> 8) == 0u && (T.ng.y >> 8) == 0u && T.sp <= 0; }
+
+RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, TravW &T) {
+    RT1W_TRAV_COUNT(0);
+    T.s.ix = rcp_capped(r.dx), T.s.iy = rcp_capped(r.dy), T.s.iz = rcp_capped(r.dz);
+    T.s.ox = -__double2float_rn(r.ox) * T.s.ix, T.s.oy = -__double2float_rn(r.oy) * T.s.iy, T.s.oz = -__double2float_rn(r.oz) * T.s.iz;
+    T.best = CUDART_INF, T.bestf = CUDART_INF_F, T.best_leaf = -1, T.sp = 0;
+    T.oct = (T.s.ix >= 0.0f ? 1u : 0u) | (T.s.iy >= 0.0f ? 2u : 0u) | (T.s.iz >= 0.0f ? 4u : 0u);
+    T.ng = make_uint2(0u, 0x8000u); // the root: "child 0 of nothing" (imask 0: index = base + 0)
+    T.lg = make_uint2(0u, 0u);
+}
+
+// one node: fetch, test the eight child boxes, split the hits into the interior group and the leaf group
+RT1W_DEV void wide_visit(const SceneView &sc, uint32_t node, TravW &T) {
+    const uint4 *n = sc.wide_nodes + 5u * size_t(node);
+    const uint4 w0 = __ldg(n), w1 = __ldg(n + 1), w2 = __ldg(n + 2), w3 = __ldg(n + 3), w4 = __ldg(n + 4);
+    const uint32_t em = w0.w; // step exponents x, y, z and imask, one byte each
+    const float ax = __uint_as_float((em & 0xffu) << 23) * T.s.ix, ay = __uint_as_float((em & 0xff00u) << 15) * T.s.iy,
+                az = __uint_as_float((em & 0xff0000u) << 7) * T.s.iz;
+    const float bx = fmaf(__uint_as_float(w0.x), T.s.ix, T.s.ox), by = fmaf(__uint_as_float(w0.y), T.s.iy, T.s.oy),
+                bz = fmaf(__uint_as_float(w0.z), T.s.iz, T.s.oz);
+    // words of four bytes (slots 0-3, 4-7): lo.x = w2.xy, lo.y = w2.zw, lo.z = w3.xy, hi.x = w3.zw, hi.y = w4.xy, hi.z = w4.zw
+    const bool px = (T.oct & 1u) != 0u, py = (T.oct & 2u) != 0u, pz = (T.oct & 4u) != 0u;
+    const uint32_t nx[2] = {px ? w2.x : w3.z, px ? w2.y : w3.w}, fx[2] = {px ? w3.z : w2.x, px ? w3.w : w2.y};
+    const uint32_t ny[2] = {py ? w2.z : w4.x, py ? w2.w : w4.y}, fy[2] = {py ? w4.x : w2.z, py ? w4.y : w2.w};
+    const uint32_t nz[2] = {pz ? w3.x : w4.z, pz ? w3.y : w4.w}, fz[2] = {pz ? w4.z : w3.x, pz ? w4.w : w3.y};
+    uint32_t hits = 0u;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int h = s >> 2, sh = 8 * (s & 3);
+        const float tnx = fmaf(float((nx[h] >> sh) & 0xffu), ax, bx), tfx = fmaf(float((fx[h] >> sh) & 0xffu), ax, bx);
+        const float tny = fmaf(float((ny[h] >> sh) & 0xffu), ay, by), tfy = fmaf(float((fy[h] >> sh) & 0xffu), ay, by);
+        const float tnz = fmaf(float((nz[h] >> sh) & 0xffu), az, bz), tfz = fmaf(float((fz[h] >> sh) & 0xffu), az, bz);
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, T.bestf)) * 1.0000005f; // conservative w.r.t. the f64 primitive solve, as `slab`
+        if (tn <= tf) hits |= 1u << s;
+    }
+    const uint32_t imask = em >> 24, lmask = w1.z & 0xffu; // empty slots are in neither
+    T.ng = make_uint2(w1.x, (octant_order(hits & imask, T.oct) << 8) | imask);
+    T.lg = make_uint2(w1.y, (octant_order(hits & lmask, T.oct) << 8) | lmask);
+}
+
+// the nearest pending interior child (of this node, else of the most recent node with children left)
+RT1W_DEV void trav_step_interior(const SceneView &sc, TravW &T, uint2 *stack, int stride, uint2 *overflow) {
+    RT1W_TRAV_COUNT(1);
+#ifdef RT1W_COUNT_TRAV
+    if (int(threadIdx.x & 31) == __ffs(int(__activemask())) - 1) RT1W_TRAV_COUNT(3);
+#endif
+    if ((T.ng.y >> 8) == 0u) {
+        --T.sp;
+        T.ng = T.sp < kStackSmem ? stack[T.sp * stride] : overflow[T.sp - kStackSmem];
+    }
+    const uint32_t v = 23u - uint32_t(__clz(int(T.ng.y))); // highest pending priority (bits 8..15)
+    const uint32_t slot = v ^ T.oct;
+    const uint32_t node = T.ng.x + uint32_t(__popc(T.ng.y & ((1u << slot) - 1u))); // interior children below `slot` (imask: bits 0..7)
+    T.ng.y &= ~(0x100u << v);
+    if ((T.ng.y >> 8) != 0u) { // its siblings wait on the stack
+        if (T.sp < kStackSmem) stack[T.sp * stride] = T.ng;
+        else overflow[T.sp - kStackSmem] = T.ng;
+        ++T.sp;
+    }
+    wide_visit(sc, node, T);
+}
+
+// the leaf slots the last node test hit, nearest first: f64 solves
+template <bool EXACT, bool MEDIA>
+RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng &mr, TravW &T, const uint2 *, int, const uint2 *) {
+    uint32_t pending = T.lg.y >> 8;
+    const uint32_t lmask = T.lg.y & 0xffu;
+    while (pending != 0u) {
+        const uint32_t v = 31u - uint32_t(__clz(int(pending)));
+        pending &= ~(1u << v);
+        const uint32_t slot = v ^ T.oct;
+        const int leaf = int(T.lg.x + uint32_t(__popc(lmask & ((1u << slot) - 1u))));
+        uint32_t box_sides = 0u;
+        do {
+            double t;
+            int side = 0;
+            RT1W_TRAV_COUNT(2);
+            if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + leaf, leaf, r, T.best, mr, t, box_sides, side)) {
+                T.best = t, T.best_leaf = leaf | (side << kLeafBits);
+                T.bestf = __double2float_ru(t);
+            }
+        } while (box_sides != 0u);
+    }
+    T.lg.y = lmask;
+}
+
+template <bool EXACT, bool MEDIA>
+RT1W_DEV bool closest_hit_wide(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
+    uint2 overflow[kStackLocal];
+    TravW T;
+    trav_begin(sc, r, T);
+    for (;;) {
+        while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, overflow);
+        if (!trav_at_leaf(T)) break;
+        trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, overflow);
     }
     t_best = T.best, leaf_best = T.best_leaf;
     return T.best_leaf >= 0;

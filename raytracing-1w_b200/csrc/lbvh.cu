@@ -180,6 +180,7 @@ cudaError_t build_lbvh(const float *h_boxes, size_t n_prims, cudaStream_t stream
                        std::vector<uint32_t> &prim_order, int *depth) {
     const int n = int(n_prims);
     *d_nodes = nullptr, *n_nodes = 0, *depth = 0;
+    cudaGetLastError(); // the launches below are checked with cudaGetLastError: start from a clean slate
     if (n < 2) return cudaErrorInvalidValue;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (size_t i = 0; i < n_prims; ++i)

@@ -252,7 +252,8 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
 // FLAT: scan the primitive list staged in shared memory (small scenes) instead of walking the BVH.
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 // RICH: some texture is not a SolidColor (else checker / Perlin / image code is compiled out: a third of the kernel).
-template <bool FLAT, bool MEDIA, bool RICH>
+// WIDE (BVH scenes): walk the compressed 8-wide tree (bvh8.h) instead of the binary one.
+template <bool FLAT, bool MEDIA, bool RICH, bool WIDE>
 __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLAT, MEDIA))
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
@@ -357,8 +358,9 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
-            hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kThreads, skip_leaf, h.t, h.leaf)
-                       : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
+            hit = FLAT   ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kThreads, skip_leaf, h.t, h.leaf)
+                  : WIDE ? closest_hit_wide<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf)
+                         : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
             if (hit) {
                 h.meta = FLAT ? s_flat[0].prims[h.leaf & kLeafMask].meta : __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
                 mat_type = int((h.meta >> 8) & 15u);
@@ -440,7 +442,14 @@ struct __align__(16) RingRay { // 64 bytes: a ray and the state of its path, bet
 };
 static_assert(sizeof(RingRay) == 64, "RingRay must be 4 x 16 bytes");
 
-template <bool MEDIA>
+template <bool WIDE> struct TravOf {
+    using type = Trav;
+};
+template <> struct TravOf<true> {
+    using type = TravW;
+};
+
+template <bool MEDIA, bool WIDE>
 __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     k_wave_bvh(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
@@ -508,8 +517,8 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     Ray r;
     RayC c;
     f3 thr;
-    Trav T;
-    T.ref = kTravDone;
+    typename TravOf<WIDE>::type T;
+    trav_reset(T);
     for (;;) {
         // ---- produce: one 32-item block -> scatter / generate with the whole warp -> surviving rays into the ring
         if (more && ring_cnt <= uint32_t(kRing - 32)) {
@@ -576,11 +585,11 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
         for (int step = 0; step < RT1W_INNER_STEPS; ++step) {
             const bool interior = has_ray && trav_interior(T);
             const unsigned walking = __ballot_sync(0xffffffffu, interior);
-            const unsigned at_leaf = __ballot_sync(0xffffffffu, has_ray && !interior && !trav_done(T));
+            const unsigned at_leaf = __ballot_sync(0xffffffffu, has_ray && trav_at_leaf(T));
             if (walking == 0u || __popc(at_leaf) >= RT1W_LEAF_LANES) break; // every round steps or solves: it always makes progress
             if (interior) trav_step_interior(a.sc, T, stack, kWaveThreads, overflow);
         }
-        if (has_ray && !trav_interior(T) && !trav_done(T)) {
+        if (has_ray && trav_at_leaf(T)) {
             MediumRng mr = {0, 0, 0, 0, 0};
             if (MEDIA) { // only ConstantMedium candidates draw random numbers inside the traversal (constant_medium.rs:85)
                 path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
@@ -660,8 +669,9 @@ __global__ void __launch_bounds__(kExtendThreads) k_trace(const __grid_constant_
         mr.c0 = uint32_t(i), mr.c1 = uint32_t(uint64_t(i) >> 32), mr.c2 = RNG_TRACE_MEDIUM, mr.k0 = seed_lo, mr.k1 = seed_hi;
         double t;
         int leaf;
-        const bool hit = flat ? closest_hit_flat<true, true>(sc, s_flat, r, mr, s_tn + threadIdx.x, kExtendThreads, -1, t, leaf)
-                              : closest_hit<true, true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
+        const bool hit = flat      ? closest_hit_flat<true, true>(sc, s_flat, r, mr, s_tn + threadIdx.x, kExtendThreads, -1, t, leaf)
+                         : sc.wide ? closest_hit_wide<true, true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf)
+                                   : closest_hit<true, true>(sc, r, mr, s_stack + threadIdx.x, kExtendThreads, t, leaf);
         HitInfo h;
         if (hit) h = finalize_hit<true>(sc.prims + (leaf & kLeafMask), sc.frames, leaf >> kLeafBits, r, t);
         if (prim_id) prim_id[i] = hit ? sc.prim_id[leaf & kLeafMask] + (leaf >> kLeafBits) : -1; // a box: its first rectangle + the side
@@ -824,11 +834,18 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     if (args.rp.flags & RT1W_FLAG_BVH_LOCKSTEP) persistent = false;
     if (args.rp.flags & RT1W_FLAG_BVH_PERSISTENT) persistent = true;
     const bool rich = args.sc.rich_textures != 0;
-    const WaveKernel kernel = flat ? (media ? (rich ? k_wave<true, true, true> : k_wave<true, true, false>)
-                                            : (rich ? k_wave<true, false, true> : k_wave<true, false, false>))
-                              : persistent ? (media ? k_wave_bvh<true> : k_wave_bvh<false>)
-                                           : (media ? (rich ? k_wave<false, true, true> : k_wave<false, true, false>)
-                                                    : (rich ? k_wave<false, false, true> : k_wave<false, false, false>));
+    bool wide = args.sc.wide != 0 && args.sc.wide_nodes != nullptr;
+    if ((args.rp.flags & RT1W_FLAG_BVH_BINARY) || args.sc.wide_nodes == nullptr) wide = false;
+    else if (args.rp.flags & RT1W_FLAG_BVH_WIDE) wide = true;
+    const WaveKernel flat_kernel = media ? (rich ? k_wave<true, true, true, false> : k_wave<true, true, false, false>)
+                                         : (rich ? k_wave<true, false, true, false> : k_wave<true, false, false, false>);
+    const WaveKernel lockstep_kernel =
+        wide ? (media ? (rich ? k_wave<false, true, true, true> : k_wave<false, true, false, true>)
+                      : (rich ? k_wave<false, false, true, true> : k_wave<false, false, false, true>))
+             : (media ? (rich ? k_wave<false, true, true, false> : k_wave<false, true, false, false>)
+                      : (rich ? k_wave<false, false, true, false> : k_wave<false, false, false, false>));
+    const WaveKernel persistent_kernel = wide ? (media ? k_wave_bvh<true, true> : k_wave_bvh<false, true>) : (media ? k_wave_bvh<true, false> : k_wave_bvh<false, false>);
+    const WaveKernel kernel = flat ? flat_kernel : (persistent ? persistent_kernel : lockstep_kernel);
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
     // The Perlin tables ride on top of the kernel's static shared memory: beyond 48 KB in total the kernel has to opt in,
     // and a scene with more tables than fit reads them from global memory instead (perlin.rs:7-12 keeps them on the heap).

@@ -28,7 +28,8 @@ def test_one_device_multi_context_equals_plain_context(rt, gpu_ctx):
     assert ctx.comm() == (0, 1, 1)
     sc = api.Scene(ctx, hs.desc)
     b, _, sb = sc.render(cam, p)
-    assert sa.rays == sb.rays and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+    ok = np.isfinite(a) & np.isfinite(b)
+    assert sa.rays == sb.rays and np.allclose(a[ok], b[ok], rtol=1e-4, atol=1e-4)  # (fp32 atomic sums: order varies from run to run)
     sc.close(), ctx.close(), plain.close()
 
 

@@ -44,8 +44,8 @@ def test_stress_scene_matches_oracle(rt, oracle, gpu_ctx, monkeypatch, n_spheres
 
 
 def test_stress_builders_and_kernels_agree(rt, gpu_ctx, monkeypatch):
-    """Same closest hits from both trees and the same image from both wave kernels (Philox draws are keyed by the path,
-    not by the traversal), at a size where every combination is cheap."""
+    """Same closest hits from both builders' trees and the same image from both wave kernels and both tree layouts (binary /
+    8-wide; Philox draws are keyed by the path, not by the traversal), at a size where every combination is cheap."""
     api = rt.api
     hs = api.HostScene("stress", seed=1, stress_spheres=300_000)
     cam = hs.camera()
@@ -62,13 +62,14 @@ def test_stress_builders_and_kernels_agree(rt, gpu_ctx, monkeypatch):
         monkeypatch.delenv("RT1W_BVH_BUILDER")
         out[builder] = gsc.trace_closest(rays, seed=3)
         for flag in (api.FLAG_BVH_LOCKSTEP, api.FLAG_BVH_PERSISTENT):
-            imgs[builder, flag] = gsc.render(cam, hs.params(width=160, spp=8, seed=2, flags=flag))
+            for layout in (api.FLAG_BVH_BINARY, api.FLAG_BVH_WIDE):
+                imgs[builder, flag, layout] = gsc.render(cam, hs.params(width=160, spp=8, seed=2, flags=flag | layout))
         gsc.close()
     a, b = out["lbvh"], out["sah"]
     same = a[0] == b[0]
     assert same.mean() > 0.9999  # (two spheres at the same distance within f64 rounding may resolve either way)
     assert np.array_equal(a[1][same], b[1][same]) and np.array_equal(a[2][same], b[2][same])
-    ref_img, _, ref_st = imgs["sah", api.FLAG_BVH_LOCKSTEP]
+    ref_img, _, ref_st = imgs["sah", api.FLAG_BVH_LOCKSTEP, api.FLAG_BVH_BINARY]
     for key, (img, _, st) in imgs.items():
         assert st.rays == ref_st.rays, key
         ok = np.isfinite(img) & np.isfinite(ref_img)

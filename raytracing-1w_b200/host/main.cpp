@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "../../include/rt1w.h"
 #include "scenes.hpp"
 
@@ -86,10 +88,18 @@ int main(int argc, char **argv) {
 
     rt1w_context *ctx = nullptr;
     if (gpus > 1) {
-        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); // stdout is the image (main.rs:953): NCCL's version / debug lines must not land in it
+        // stdout is the image (main.rs:953): NCCL writes its version / debug lines to stdout while the communicator is set
+        // up, so file descriptor 1 points at stderr for the duration of that call
         std::vector<int32_t> ids;
         for (int g = 0; g < gpus; ++g) ids.push_back(device + g);
-        if (rt1w_context_create_multi(ids.data(), gpus, &ctx) != RT1W_OK) return fail("rt1w_context_create_multi");
+        std::fflush(stdout);
+        const int saved_stdout = dup(1);
+        dup2(2, 1);
+        const rt1w_status st = rt1w_context_create_multi(ids.data(), gpus, &ctx);
+        std::fflush(stdout);
+        dup2(saved_stdout, 1);
+        close(saved_stdout);
+        if (st != RT1W_OK) return fail("rt1w_context_create_multi");
     } else if (rt1w_context_create(device, &ctx) != RT1W_OK) {
         return fail("rt1w_context_create");
     }

@@ -131,6 +131,7 @@ pub struct rt1w_render_stats {
     pub kernel_ms: [f64; 7],
     pub kernel_launches: [u64; 7],
 }
+pub const RT1W_COMM_ID_BYTES: usize = 128;
 pub enum rt1w_context {}
 pub enum rt1w_scene {}
 
@@ -139,6 +140,14 @@ extern "C" {
     pub fn rt1w_last_error() -> *const c_char;
     pub fn rt1w_context_create(device_id: i32, out: *mut *mut rt1w_context) -> i32;
     pub fn rt1w_context_destroy(ctx: *mut rt1w_context);
+    // Multi-GPU (include/rt1w.h "Multi-GPU"): sample ranges sharded inside the library, one ncclReduce per render call.
+    // (a) this process drives n devices: every later call on the context / its scenes is unchanged
+    pub fn rt1w_context_create_multi(device_ids: *const i32, n: i32, out: *mut *mut rt1w_context) -> i32;
+    // (b) one process per device: rank 0 makes the id, the host side ships it, every rank joins
+    pub fn rt1w_comm_unique_id(out_id: *mut u8, capacity: usize) -> i32; // capacity >= RT1W_COMM_ID_BYTES
+    pub fn rt1w_context_comm_init(ctx: *mut rt1w_context, id: *const u8, n_ranks: i32, rank: i32) -> i32;
+    pub fn rt1w_context_get_comm(ctx: *const rt1w_context, rank: *mut i32, n_ranks: *mut i32, n_local_devices: *mut i32) -> i32;
+    pub fn rt1w_shard_sample_range(rank: i32, n_ranks: i32, sample_begin: i32, sample_end: i32, out_begin: *mut i32, out_end: *mut i32);
     pub fn rt1w_scene_create(ctx: *mut rt1w_context, desc: *const rt1w_scene_desc, out: *mut *mut rt1w_scene) -> i32;
     pub fn rt1w_scene_destroy(scene: *mut rt1w_scene);
     pub fn rt1w_render(

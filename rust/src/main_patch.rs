@@ -28,8 +28,16 @@ pub fn render_and_print(
         }
     }
 
+    // RT1W_GPUS=n: devices 0..n-1 render together (rt1w_context_create_multi: the library shards the sample range over
+    // them and adds the radiance sums with one ncclReduce); nothing below changes
+    let gpus: i32 = std::env::var("RT1W_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(1);
     let mut ctx = ptr::null_mut();
-    check(unsafe { rt1w_context_create(0, &mut ctx) });
+    if gpus > 1 {
+        let ids: Vec<i32> = (0..gpus).collect();
+        check(unsafe { rt1w_context_create_multi(ids.as_ptr(), gpus, &mut ctx) });
+    } else {
+        check(unsafe { rt1w_context_create(0, &mut ctx) });
+    }
     let mut scene = ptr::null_mut();
     check(unsafe { rt1w_scene_create(ctx, &b.desc(), &mut scene) });
 

@@ -494,7 +494,11 @@ struct TravW {
 };
 // The wide tree's stack lives in shared memory only (one entry per LEVEL: 16 entries reach deeper than any tree the
 // collapse of a <= 62-level binary tree is used for; deeper wide trees fall back to the binary traversal, api.cu).
-constexpr int kWideMaxDepth = kStackSmem - 2;
+#ifndef RT1W_WIDE_STACK
+#define RT1W_WIDE_STACK 12 // entries per thread: with 12 the persistent kernel's CTA fits the 132 KB shared-memory carveout four times (more L1 for the nodes)
+#endif
+constexpr int kWideStack = RT1W_WIDE_STACK;
+constexpr int kWideMaxDepth = kWideStack - 2;
 
 // 8-bit slot mask -> priority order: bit (s ^ oct) of the result = bit s of m
 RT1W_DEV uint32_t octant_order(uint32_t m, uint32_t oct) {

@@ -427,9 +427,10 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
 #define RT1W_LEAF_LANES 24 // a round's interior steps stop once this many lanes wait at a leaf
 #endif
 // the 8-wide tree: a third of the steps per ray, each four times the work - rays end (and lanes idle) after fewer steps, so
-// the rounds are shorter (measured on the 1 M-sphere scene: 32 steps 547 Mrays/s, 8 steps 794, 4 steps 694)
+// the rounds are shorter (measured on the 1 M-sphere scene: 32 steps 547 Mrays/s, 8 steps 794, 4 steps 694), and a lane takes
+// two steps per vote (4 votes of 2 steps: 910 against 888 Mrays/s for 8 votes of 1)
 #ifndef RT1W_INNER_STEPS_WIDE
-#define RT1W_INNER_STEPS_WIDE 8
+#define RT1W_INNER_STEPS_WIDE 4
 #endif
 #ifndef RT1W_LEAF_LANES_WIDE
 #define RT1W_LEAF_LANES_WIDE 24
@@ -461,7 +462,7 @@ template <bool MEDIA, bool WIDE>
 __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     k_wave_bvh(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
-    __shared__ uint2 s_stack[kStackSmem * kWaveThreads];
+    __shared__ uint2 s_stack[(WIDE ? kWideStack : kStackSmem) * kWaveThreads];
     __shared__ RingRay s_ring[(kWaveThreads / 32) * kRing];
     __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
     __shared__ unsigned int s_traced, s_next;
@@ -597,6 +598,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
             const unsigned at_leaf = __ballot_sync(0xffffffffu, has_ray && trav_at_leaf(T));
             if (walking == 0u || __popc(at_leaf) >= kLeafLanes) break; // every round steps or solves: it always makes progress
             if (interior) trav_step_interior(a.sc, T, stack, kWaveThreads, overflow);
+            if (WIDE && interior && trav_interior(T)) trav_step_interior(a.sc, T, stack, kWaveThreads, overflow); // a second step on the same vote
         }
         if (has_ray && trav_at_leaf(T)) {
             MediumRng mr = {0, 0, 0, 0, 0};

@@ -431,27 +431,73 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     }
     const size_t n = dev.size();
     if (n >= size_t(1) << kLeafBits) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^28 primitives");
-    std::vector<double> bmin(3 * n), bmax(3 * n);
     for (size_t i = 0; i < n; ++i)
-        for (int k = 0; k < 3; ++k) {
-            bmin[3 * i + k] = dev[i].bbox_min[k], bmax[3 * i + k] = dev[i].bbox_max[k];
-            if (!std::isfinite(bmin[3 * i + k]) || !std::isfinite(bmax[3 * i + k]))
+        for (int k = 0; k < 3; ++k)
+            if (!std::isfinite(dev[i].bbox_min[k]) || !std::isfinite(dev[i].bbox_max[k]))
                 return fail(RT1W_ERR_INVALID, "No bounding box in bvh_node constructor. (bvh.rs:65-67): non-finite primitive bounds");
+    // Primitives whose box contains every other primitive's box - final_scene's 5000-unit fog sphere (main.rs:734-745) -
+    // stay OUT of the tree: no box test ever culls them, in the tree they are one more level and one divergent leaf visit
+    // for every ray.  They go to the end of the primitive array and are tested once per ray after the traversal, by all
+    // lanes of the warp together (kernels.cuh: hit_globals).  RT1W_GLOBAL_PRIMS=0 keeps them in the tree (A/B, tests).
+    size_t n_global = 0;
+    const char *glob_env = std::getenv("RT1W_GLOBAL_PRIMS");
+    if (!flat && n >= 8 && !(glob_env && std::strcmp(glob_env, "0") == 0)) {
+        constexpr size_t kMaxGlobal = 4;
+        std::vector<char> is_global(n, 0);
+        for (size_t round = 0; round < kMaxGlobal; ++round) { // the box of all the OTHER primitives still in the tree, per candidate, from the two extremes of each bound
+            double lo1[3], lo2[3], hi1[3], hi2[3];
+            size_t lo_at[3], hi_at[3];
+            for (int k = 0; k < 3; ++k) lo1[k] = lo2[k] = INFINITY, hi1[k] = hi2[k] = -INFINITY, lo_at[k] = hi_at[k] = n;
+            for (size_t i = 0; i < n; ++i) {
+                if (is_global[i]) continue;
+                for (int k = 0; k < 3; ++k) {
+                    const double a = dev[i].bbox_min[k], b = dev[i].bbox_max[k];
+                    if (a < lo1[k]) lo2[k] = lo1[k], lo1[k] = a, lo_at[k] = i;
+                    else if (a < lo2[k]) lo2[k] = a;
+                    if (b > hi1[k]) hi2[k] = hi1[k], hi1[k] = b, hi_at[k] = i;
+                    else if (b > hi2[k]) hi2[k] = b;
+                }
+            }
+            size_t found = n;
+            for (size_t i = 0; i < n && found == n; ++i) {
+                if (is_global[i]) continue;
+                bool contains = true;
+                for (int k = 0; k < 3 && contains; ++k) {
+                    const double olo = lo_at[k] == i ? lo2[k] : lo1[k], ohi = hi_at[k] == i ? hi2[k] : hi1[k];
+                    contains = dev[i].bbox_min[k] <= olo && dev[i].bbox_max[k] >= ohi;
+                }
+                if (contains) found = i;
+            }
+            if (found == n) break;
+            is_global[found] = 1, ++n_global;
         }
+        if (n_global > 0) { // stable: tree primitives first, globals last (primitive ids travel with them)
+            std::vector<rt1w_flat_prim> d2;
+            std::vector<int32_t> id2;
+            for (int pass = 0; pass < 2; ++pass)
+                for (size_t i = 0; i < n; ++i)
+                    if (int(is_global[i]) == pass) d2.push_back(dev[i]), id2.push_back(dev_first_id[i]);
+            dev.swap(d2), dev_first_id.swap(id2);
+        }
+    }
+    const size_t nb = n - n_global; // primitives in the tree
+    std::vector<double> bmin(3 * nb), bmax(3 * nb);
+    for (size_t i = 0; i < nb; ++i)
+        for (int k = 0; k < 3; ++k) bmin[3 * i + k] = dev[i].bbox_min[k], bmax[3 * i + k] = dev[i].bbox_max[k];
     // Builder: binned SAH on the host (best trees; seconds for a million primitives) or, for big scenes, a linear BVH
     // on the device (lbvh.cu; milliseconds).  RT1W_BVH_BUILDER=sah|lbvh overrides the size rule (tuning, tests).
     BvhBuildResult bvh;
     BvhNode32 *d_lbvh_nodes = nullptr;
     size_t n_bvh_nodes = 0;
-    bool use_lbvh = n >= size_t(kLbvhFromPrims);
-    if (const char *env = std::getenv("RT1W_BVH_BUILDER")) use_lbvh = std::strcmp(env, "lbvh") == 0 ? n >= 2 : (std::strcmp(env, "sah") == 0 ? false : use_lbvh);
+    bool use_lbvh = nb >= size_t(kLbvhFromPrims);
+    if (const char *env = std::getenv("RT1W_BVH_BUILDER")) use_lbvh = std::strcmp(env, "lbvh") == 0 ? nb >= 2 : (std::strcmp(env, "sah") == 0 ? false : use_lbvh);
     if (use_lbvh) {
         RT1W_CUDA(cudaSetDevice(ctx->device));
-        std::vector<float> boxes(6 * n);
-        const double pad = traversal_pad(bmin.data(), bmax.data(), n);
-        for (size_t i = 0; i < n; ++i) conservative_box(dev[i].bbox_min, dev[i].bbox_max, &boxes[6 * i], &boxes[6 * i + 3], pad);
+        std::vector<float> boxes(6 * nb);
+        const double pad = traversal_pad(bmin.data(), bmax.data(), nb);
+        for (size_t i = 0; i < nb; ++i) conservative_box(dev[i].bbox_min, dev[i].bbox_max, &boxes[6 * i], &boxes[6 * i + 3], pad);
         int depth = 0;
-        cudaError_t e = build_lbvh(boxes.data(), n, ctx->stream, &d_lbvh_nodes, &n_bvh_nodes, bvh.prim_order, &depth);
+        cudaError_t e = build_lbvh(boxes.data(), nb, ctx->stream, &d_lbvh_nodes, &n_bvh_nodes, bvh.prim_order, &depth);
         if (e != cudaSuccess) return fail_cuda("device BVH build", e);
         bvh.depth = depth;
         if (depth > kStackSmem + kStackLocal - 2) { // many coincident centroids: let the SAH builder split by index instead
@@ -460,7 +506,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
         }
     }
     if (!use_lbvh) {
-        build_sah_bvh(bmin.data(), bmax.data(), n, kMaxLeaf, bvh);
+        build_sah_bvh(bmin.data(), bmax.data(), nb, kMaxLeaf, bvh);
         n_bvh_nodes = bvh.nodes.size();
     }
     struct NodeGuard { // the device nodes belong to the scene once it exists
@@ -479,13 +525,14 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
             cudaFree(d_lbvh_nodes), d_lbvh_nodes = nullptr;
         }
         collapse_to_bvh8(bvh.nodes.data(), bvh.nodes.size(), wide);
-        if (wide.leaf_remap.size() != n) return fail(RT1W_ERR_STATE, "wide BVH collapse lost primitives");
-        std::vector<uint32_t> new_of_old(n), order(n);
-        for (size_t i = 0; i < n; ++i) new_of_old[wide.leaf_remap[i]] = uint32_t(i), order[i] = bvh.prim_order[wide.leaf_remap[i]];
+        if (wide.leaf_remap.size() != nb) return fail(RT1W_ERR_STATE, "wide BVH collapse lost primitives");
+        std::vector<uint32_t> new_of_old(nb), order(nb);
+        for (size_t i = 0; i < nb; ++i) new_of_old[wide.leaf_remap[i]] = uint32_t(i), order[i] = bvh.prim_order[wide.leaf_remap[i]];
         for (BvhNode32 &nd : bvh.nodes)
             if (nd.count != 0) nd.left_first = new_of_old[nd.left_first];
         bvh.prim_order.swap(order);
     }
+    for (size_t g = nb; g < n; ++g) bvh.prim_order.push_back(uint32_t(g)); // the global primitives: leaf indices nb .. n - 1
     std::vector<DPrim> dprims(n);
     std::vector<int32_t> prim_id(n);
     for (size_t i = 0; i < n; ++i) {
@@ -628,6 +675,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     v.materials = s->d_materials, v.textures = s->d_textures, v.perlins = s->d_perlins;
     v.images = s->d_images, v.image_dims = s->d_image_dims, v.lights = s->d_lights;
     v.n_lights = int32_t(low.lights.size()), v.has_lights = low.has_lights ? 1 : 0;
+    v.n_global = int32_t(n_global);
     v.n_prims = int32_t(n), v.n_nodes = int32_t(n_bvh_nodes), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
     v.flat = flat ? 1 : 0;
     v.wide_nodes = s->d_wide_nodes;
@@ -647,7 +695,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     s->info.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     s->info.sah_cost = bvh.sah_cost;
     s->info.n_wide_nodes = int32_t(wide.nodes.size()), s->info.wide_depth = wide.depth, s->info.wide_default = v.wide;
-    s->info.wide_children = wide.avg_children;
+    s->info.wide_children = wide.avg_children, s->info.n_global_prims = int32_t(n_global);
     *out = s.release();
     return RT1W_OK;
 }

@@ -47,6 +47,7 @@ struct SceneView {
     const DLight *lights;
     int32_t n_lights, has_lights;
     int32_t n_prims, n_nodes, n_perlins, n_frames;
+    int32_t n_global; // the last n_global primitives are in no tree: every ray tests them (hit_globals)
     int32_t flat; // scan the primitive list (closest_hit_flat) instead of walking the BVH
     int32_t wide; // BVH scenes: walk the 8-wide tree by default (render flags may force either layout)
     int32_t rich_textures; // some texture is not a SolidColor
@@ -455,6 +456,21 @@ RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng 
     trav_pop(T, stack, stride, overflow);
 }
 
+// The primitives that are in no tree (api.cu: their box contains every other primitive's, e.g. a fog sphere around the
+// whole scene): tested after the traversal, against the best hit it found - the whole warp at once.
+template <bool EXACT, bool MEDIA>
+RT1W_DEV void hit_globals(const SceneView &sc, const Ray &r, const MediumRng &mr, double &best, int &best_leaf) {
+    for (int g = sc.n_prims - sc.n_global; g < sc.n_prims; ++g) {
+        uint32_t box_sides = 0u;
+        do {
+            double t;
+            int side = 0;
+            RT1W_TRAV_COUNT(2);
+            if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + g, g, r, best, mr, t, box_sides, side)) best = t, best_leaf = g | (side << kLeafBits);
+        } while (box_sides != 0u);
+    }
+}
+
 // while-while traversal to the end: every lane descends to its next leaf before any lane runs the (f64)
 // primitive tests, so those run with most of the warp converged.
 template <bool EXACT, bool MEDIA>
@@ -466,6 +482,7 @@ RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr
         while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, overflow);
         if (!trav_done(T)) trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, overflow);
     }
+    hit_globals<EXACT, MEDIA>(sc, r, mr, T.best, T.best_leaf);
     t_best = T.best, leaf_best = T.best_leaf;
     return T.best_leaf >= 0;
 }
@@ -619,6 +636,7 @@ RT1W_DEV bool closest_hit_wide(const SceneView &sc, const Ray &r, const MediumRn
         if (!trav_at_leaf(T)) break;
         trav_step_leaf<EXACT, MEDIA>(sc, r, mr, T, stack, stride, nullptr);
     }
+    hit_globals<EXACT, MEDIA>(sc, r, mr, T.best, T.best_leaf);
     t_best = T.best, leaf_best = T.best_leaf;
     return T.best_leaf >= 0;
 }

@@ -615,6 +615,14 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
             HitRec h;
             if (fin) {
                 has_ray = false;
+                if (a.sc.n_global > 0) { // the primitives that are in no tree
+                    MediumRng mr = {0, 0, 0, 0, 0};
+                    if (MEDIA) {
+                        path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
+                        mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
+                    }
+                    hit_globals<false, MEDIA>(a.sc, r, mr, T.best, T.best_leaf);
+                }
                 const bool hit = T.best_leaf >= 0;
                 h.t = T.best, h.leaf = T.best_leaf;
                 int mat_type = RT1W_MAT_NONE;

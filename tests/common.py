@@ -147,3 +147,17 @@ def check_render_parity(api, gsc, osc, cam, make_params, spp, stat_clamp=20.0, f
     rpp_g, rpp_o = g_st.rays / g_st.paths, oa_st.rays / oa_st.paths
     assert abs(rpp_g - rpp_o) <= 0.02 * rpp_o, f"rays/path gpu {rpp_g:.3f} oracle {rpp_o:.3f}"
     return g_st, oa_st
+
+
+def check_same_render(a, b, label=""):
+    """Two renders of the same paths by two differently compiled kernels (lockstep / persistent, binary / 8-wide): the same
+    closest hits, so the same image - except that the two instantiations may contract an f64 expression differently, and a
+    last-bit difference in one hit distance sends a deep path (depth up to 50) another way: a handful of rays per million.
+    a, b: (rgb_sum, stat, RenderStats)."""
+    (ia, _, sa), (ib, _, sb) = a, b
+    assert sa.paths == sb.paths, label
+    assert abs(float(sa.rays) - float(sb.rays)) <= 1e-4 * float(sa.rays), f"{label}: {sa.rays} vs {sb.rays} rays"
+    ok = np.isfinite(ia) & np.isfinite(ib)
+    close = np.isclose(ia, ib, rtol=1e-3, atol=1e-3) | ~ok
+    assert close.all(axis=2).mean() >= 0.999, f"{label}: {(~close.all(axis=2)).sum()} pixels differ"
+    assert abs(np.nansum(ia) - np.nansum(ib)) <= 2e-3 * abs(np.nansum(ia)), label

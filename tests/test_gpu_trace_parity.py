@@ -195,3 +195,28 @@ def test_moving_spheres_at_extrapolated_times(rt, oracle, gpu_ctx):
           f"{differ.mean():.5f} resolve differently (the sphere has left its [time0, time1] box)")
     assert differ.mean() <= 0.02
     gsc.close()
+
+
+def test_global_primitives_stay_out_of_the_tree(rt, oracle, gpu_ctx, monkeypatch):
+    """final_scene's fog - a ConstantMedium in a sphere of radius 5000 around everything (main.rs:734-745) - is in no BVH: its
+    box contains every other primitive's, so every ray tests it once, after the traversal.  Same closest hits as with the
+    sphere in the tree (`RT1W_GLOBAL_PRIMS=0`) and as the oracle's."""
+    api = rt.api
+    hs = api.HostScene("final_scene", seed=1)
+    osc = oracle.OracleScene(hs.desc)
+    out_of_tree = api.Scene(gpu_ctx, hs.desc)
+    monkeypatch.setenv("RT1W_GLOBAL_PRIMS", "0")
+    in_tree = api.Scene(gpu_ctx, hs.desc)
+    monkeypatch.delenv("RT1W_GLOBAL_PRIMS")
+    assert out_of_tree.info().n_global_prims == 1 and in_tree.info().n_global_prims == 0
+    assert out_of_tree.info().n_bvh_nodes == in_tree.info().n_bvh_nodes - 2
+    rays = make_ray_set(api, hs, osc, in_tree.prims(), 1 << 16, 700.0)
+    cache = {}
+    check_trace_parity(in_tree, osc, rays, label="final_scene, fog sphere in the tree", cache=cache)
+    check_trace_parity(out_of_tree, osc, rays, label="final_scene, fog sphere out of the tree", cache=cache)
+    a, b = out_of_tree.trace_closest(rays, seed=0x5EED), in_tree.trace_closest(rays, seed=0x5EED)
+    same = a[0] == b[0]
+    assert same[cache["trace"][5] == 0].all()
+    for k in (1, 2, 3, 4):
+        assert np.array_equal(a[k][same], b[k][same])
+    out_of_tree.close(), in_tree.close()

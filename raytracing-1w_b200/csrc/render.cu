@@ -24,6 +24,7 @@
 #include "render.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace rt1w {
@@ -47,8 +48,11 @@ constexpr int kWaveThreads = RT1W_WAVE_THREADS;
 #endif
 // CTA size and CTAs per SM of the wave kernel variants (the launch uses the same functions)
 __host__ __device__ constexpr int wave_threads(bool flat, bool media) { return flat && !media ? RT1W_FLAT_THREADS : kWaveThreads; }
+#ifndef RT1W_FLAT_PLAIN_MIN_BLOCKS
+#define RT1W_FLAT_PLAIN_MIN_BLOCKS (6 * 128 / RT1W_FLAT_THREADS)
+#endif
 __host__ __device__ constexpr int wave_min_blocks(bool flat, bool media) {
-    return flat ? (media ? RT1W_FLAT_MIN_BLOCKS : 6 * 128 / RT1W_FLAT_THREADS) : RT1W_BVH_MIN_BLOCKS + (media ? 0 : 1);
+    return flat ? (media ? RT1W_FLAT_MIN_BLOCKS : RT1W_FLAT_PLAIN_MIN_BLOCKS) : RT1W_BVH_MIN_BLOCKS + (media ? 0 : 1);
 }
 constexpr int kExtendThreads = kWaveThreads; // k_trace shares the traversal-stack geometry
 
@@ -253,7 +257,10 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
 // MEDIA: the scene has ConstantMedium primitives (their candidates draw random numbers inside the traversal).
 // RICH: some texture is not a SolidColor (else checker / Perlin / image code is compiled out: a third of the kernel).
 // WIDE (BVH scenes): walk the compressed 8-wide tree (bvh8.h) instead of the binary one.
-template <bool FLAT, bool MEDIA, bool RICH, bool WIDE>
+// PHASE: 0 = the fused wave (the product).  1 / 2 = the same wave as TWO launches, for the A/B against north_star's split
+// pipeline (RT1W_SPLIT_PIPELINE=1, tools/ab_split.sh): 1 = generate + shade only - scattered / new rays go to a staging
+// queue in HBM (64 B per work item) -, 2 = extend only - reads them back, closest hit, regroup per material.
+template <bool FLAT, bool MEDIA, bool RICH, bool WIDE, int PHASE = 0>
 __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLAT, MEDIA))
     k_wave(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem) {
     extern __shared__ __align__(16) unsigned char s_dyn[]; // Perlin tables (perlin.rs:7-12), when the scene has any
@@ -298,11 +305,12 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
     const unsigned long long path0 = ctr->next_path[slot];
     const unsigned long long left = a.rp.total_paths - min(a.rp.total_paths, path0);
     const uint32_t n_new = uint32_t(min((unsigned long long)(a.pool.capacity - min(a.pool.capacity, queued)), left));
-    const uint32_t total = off4 + n_new;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { // hand the counters over: nobody else writes these slots during this wave
+    const uint32_t total = PHASE == 2 ? ctr->split_total : off4 + n_new;
+    if (PHASE != 2 && blockIdx.x == 0 && threadIdx.x == 0) { // hand the counters over: nobody else writes these slots during this wave
         ctr->next_path[nxt] = path0 + n_new;
 #pragma unroll
         for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[clr][q] = 0;
+        if (PHASE == 1) ctr->split_total = total;
     }
     if (blockIdx.x * blockDim.x >= total) return;
 
@@ -327,7 +335,15 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
         bool alive = false, ends = false; // ends: the path is over and its pixel gets throughput * rad
         int skip_leaf = -1;               // the primitive the ray starts on
         const uint32_t off4 = lay.off4;
-        if (i < off4) { // a hit queued by the previous wave: scatter
+        if (PHASE == 2) { // the ray the shade launch left for this work item
+            if (i < lay.total) {
+                r = load_ray(a.pool.stage, i, c);
+                const float4 th4 = stream_load(a.pool.stage.t + i);
+                thr = mk3(th4.x, th4.y, th4.z);
+                skip_leaf = __float_as_int(th4.w);
+                alive = skip_leaf != -2;
+            }
+        } else if (i < off4) { // a hit queued by the previous wave: scatter
             const uint32_t off1 = lay.off1, off2 = lay.off2, off3 = lay.off3;
             const int seg = i < off1 ? 0 : (i < off2 ? 1 : (i < off3 ? 2 : 3)); // warp-uniform
             const uint32_t j = i - (seg == 0 ? 0u : (seg == 1 ? off1 : (seg == 2 ? off2 : off3)));
@@ -345,6 +361,22 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
             r = generate_ray(a, lay.gen_t0, lay.gen_w0, i - off4, c.state, c.pixel);
             thr = mk3(1.0f, 1.0f, 1.0f);
             alive = true;
+        }
+        if (PHASE == 1) { // hand the ray to the extend launch; a path that ended on the depth limit delivers its NaN throughput here
+            if (ends && !finite3(thr)) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
+            if (i < lay.total) {
+                const RayQueue &st = a.pool.stage;
+                if (alive) {
+                    stream_store(st.a + i, make_double2(r.ox, r.oy));
+                    RayB b;
+                    b.oz = r.oz, b.dx = r.dx, b.dy = r.dy;
+                    stream_store(st.b + i, b);
+                    c.dz = r.dz, c.time = r.time;
+                    stream_store(st.c + i, c);
+                }
+                stream_store(st.t + i, make_float4(thr.x, thr.y, thr.z, __int_as_float(alive ? skip_leaf : -2)));
+            }
+            continue;
         }
 
         int dest = -1;
@@ -821,6 +853,7 @@ cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask) {
         for (int q = 0; q < Q_COUNT && e == cudaSuccess; ++q)
             if ((material_mask & (1 << q)) && q != RT1W_MAT_DIFFUSE_LIGHT) e = queue_alloc(pool.mat[k][q], capacity);
     if (e == cudaSuccess) e = cudaMalloc(&pool.ctr, sizeof(Counters));
+    if (e == cudaSuccess && std::getenv("RT1W_SPLIT_PIPELINE")) e = queue_alloc(pool.stage, capacity + 4u * 32u); // (A/B only; the hit segments are padded to warps)
     if (e != cudaSuccess) {
         pool_free(pool);
         return e;
@@ -831,6 +864,7 @@ cudaError_t pool_alloc(Pool &pool, uint32_t capacity, int material_mask) {
 }
 
 void pool_free(Pool &pool) {
+    queue_free(pool.stage);
     for (int k = 0; k < 2; ++k)
         for (int q = 0; q < Q_COUNT; ++q) queue_free(pool.mat[k][q]);
     cudaFree(pool.ctr);
@@ -865,6 +899,22 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
                       : (rich ? k_wave<false, false, true, false> : k_wave<false, false, false, false>));
     const WaveKernel persistent_kernel = wide ? (media ? k_wave_bvh<true, true> : k_wave_bvh<false, true>) : (media ? k_wave_bvh<true, false> : k_wave_bvh<false, false>);
     const WaveKernel kernel = flat ? flat_kernel : (persistent ? persistent_kernel : lockstep_kernel);
+    // A/B against a split pipeline (RT1W_SPLIT_PIPELINE=1): the same wave as a shade launch + an extend launch, with the rays
+    // in HBM in between.  Instantiated for the scenes the A/B is run on: medium-free flat scenes and binary-tree scenes.
+    WaveKernel split_shade = nullptr, split_extend = nullptr;
+    if (args.pool.stage.a != nullptr && !persistent && !media && !wide) {
+        if (flat) {
+            split_shade = rich ? k_wave<true, false, true, false, 1> : k_wave<true, false, false, false, 1>;
+            split_extend = rich ? k_wave<true, false, true, false, 2> : k_wave<true, false, false, false, 2>;
+        } else {
+            split_shade = rich ? k_wave<false, false, true, false, 1> : k_wave<false, false, false, false, 1>;
+            split_extend = rich ? k_wave<false, false, true, false, 2> : k_wave<false, false, false, false, 2>;
+        }
+        if (flat) {
+            cudaFuncSetAttribute(split_shade, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(split_extend, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+    }
     if (flat) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); // scene + scan tables live in shared memory
     // The Perlin tables ride on top of the kernel's static shared memory: beyond 48 KB in total the kernel has to opt in,
     // and a scene with more tables than fit reads them from global memory instead (perlin.rs:7-12 keeps them on the heap).
@@ -937,6 +987,12 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         for (int k = 0; k < poll_every; ++k, ++wave) {
             const int slot = int(wave % 3), parity = int(wave & 1);
             mark(K_WAVE);
+            if (split_shade) {
+                if ((e = cudaLaunchKernelEx(&launch, split_shade, args, slot, parity, perlin_in_smem)) != cudaSuccess) break;
+                if ((e = cudaLaunchKernelEx(&launch, split_extend, args, slot, parity, perlin_in_smem)) != cudaSuccess) break;
+                ws.launches += 2;
+                continue;
+            }
             if ((e = cudaLaunchKernelEx(&launch, kernel, args, slot, parity, perlin_in_smem)) != cudaSuccess) break;
             ++ws.launches;
         }

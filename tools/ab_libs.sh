@@ -1,11 +1,13 @@
 #!/bin/bash
-# bench + Cornell scene throughput for the product library and every variant, interleaved twice (box-to-box and run-to-run noise)
-for rep in 1 2; do
-for lib in raytracing-1w_b200/_build/librt1w.so raytracing-1w_b200/_build/variant_*.so; do
-  [ -f "$lib" ] || continue
-  RT1W_LIB=$PWD/$lib python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" 2>&1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib'.split('/')[-1], 'Mpaths/s',round(d['value'],1),'ms/step',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1),'rays/path',round(d['rays_per_path'],4))"
-done
+# A/B of build variants (python raytracing-1w_b200/build.py --variant NAME -D...): tools/ab_libs.sh "scene:spp ..." librt1w variant_a variant_b
+SCENES=${1:-cornel_box:100}; shift
+for lib in "$@"; do
+  echo "== $lib"
+  for i in 1 2; do
+    RT1W_LIB=$PWD/raytracing-1w_b200/_build/$lib.so timeout 600 python tools/scene_perf.py $SCENES 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(' ', d['scene'], d['image'], d['spp'], 'ms', d['render_ms'], 'Mpaths/s', d['mpaths_s'], 'Mrays/s', d['mrays_s'])"
+  done
 done

@@ -46,7 +46,7 @@ struct SceneView {
     const int2 *image_dims;
     const DLight *lights;
     int32_t n_lights, has_lights;
-    int32_t n_prims, n_nodes, n_perlins, n_frames;
+    int32_t n_prims, n_nodes, n_wide, n_perlins, n_frames;
     int32_t n_global; // the last n_global primitives are in no tree: every ray tests them (hit_globals)
     int32_t flat; // scan the primitive list (closest_hit_flat) instead of walking the BVH
     int32_t wide; // BVH scenes: walk the 8-wide tree by default (render flags may force either layout)

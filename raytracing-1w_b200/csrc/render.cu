@@ -23,6 +23,7 @@
 // 288 B per segment, 7 launches per wave) ran 1.3x slower.
 #include "render.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -932,6 +933,29 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         }
     }
     if (!perlin_in_smem) perlin_bytes = 0;
+    // north_star (a): the BVH nodes "kept resident in L2".  The trees of the BASELINE scenes fit L2 many times over and are
+    // hit there anyway (L2 hit rate 93 % on the 1 M-sphere scene, whose 22 MB of wide nodes compete with 64 MB of primitives
+    // and the streaming queues); RT1W_L2_PERSIST=1 pins the node array with an access-policy window for the A/B.
+    bool l2_window = false;
+    if (!flat && std::getenv("RT1W_L2_PERSIST")) {
+        int dev = 0, max_window = 0, max_persist = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        const void *base = wide ? static_cast<const void *>(args.sc.wide_nodes) : static_cast<const void *>(args.sc.nodes);
+        const size_t bytes = wide ? size_t(args.sc.n_wide) * 80u : size_t(args.sc.n_nodes) * 32u;
+        if (max_window > 0 && max_persist > 0 && bytes > 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(size_t(max_persist), bytes));
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+            attr.accessPolicyWindow.num_bytes = std::min(bytes, size_t(max_window));
+            attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(max_persist) / double(bytes)));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            l2_window = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            if (!l2_window) cudaGetLastError();
+        }
+    }
     const int threads = wave_threads(flat, media);
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
@@ -1021,6 +1045,12 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         if (snap_ev[k]) cudaEventDestroy(snap_ev[k]);
     for (auto &m : marks) cudaEventDestroy(m.ev);
     for (auto ev : spare) cudaEventDestroy(ev);
+    if (l2_window) { // (the window is a property of the caller's stream: give it back as it was)
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+    }
     if (e != cudaSuccess) return e;
     ws.waves = wave;
     ws.rays = last->rays;

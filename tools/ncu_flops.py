@@ -1,4 +1,4 @@
-"""profiles/r02_flops.json from the captures of tools/r2_profiles.sh: per BASELINE config, the fp32 / fp64 flops per ray that
+"""profiles/r02_flops.json from the captures of tools/profiles_capture.sh: per BASELINE config, the fp32 / fp64 flops per ray that
 ncu COUNTED over all wave launches of one whole render (fadd + fmul + 2 ffma, dadd + dmul + 2 dfma; predicated-on
 threads), the thread instructions per ray, and the DRAM bytes of the steady-state launch of the `--set full` capture.
 bench.py multiplies flops per ray by the rays it counts live (SURVEY.md section 8d's secondary roofline figure).

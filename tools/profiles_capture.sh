@@ -1,8 +1,13 @@
 #!/bin/bash
-# profiles/r02_*: bench lines, the launch list of the bench command, one `ncu --set full` capture of a steady-state wave per
-# BASELINE config, and ncu-counted flops of one whole render per config (tools/ncu_flops.py turns them into profiles/r02_flops.json)
+# Round-end rehearsal on one GPU + the captures behind profiles/<TAG>_*: smoke, the GPU tests, both bench arms as the driver runs
+# them, the launch list of the bench command, one `ncu --set full` capture of a steady-state wave per BASELINE config, and
+# ncu-counted flops of one whole render per config.  Afterwards, here: tools/profiles_refresh.sh <TAG> (summaries, regions,
+# metrics, profiles/<TAG>_flops.json) and tools/ab_split.sh for the fused-vs-split A/B.
+#     gpurun --timeout 2400 -- 'bash tools/profiles_capture.sh r02'
 TAG=${1:-r02}
 mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -3
 python bench.py --impl reference > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || tail -5 gpurun_out/${TAG}_bench.err
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-configs"

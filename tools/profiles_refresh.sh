@@ -1,5 +1,5 @@
 #!/bin/bash
-# profiles/<TAG>_* from the captures of tools/r2_profiles.sh (run here, after the gpurun call has merged gpurun_out/): tools/profiles_refresh.sh r02
+# profiles/<TAG>_* from the captures of tools/profiles_capture.sh (run here, after the gpurun call has merged gpurun_out/): tools/profiles_refresh.sh r02
 TAG=${1:?tag of the gpurun_out files}
 tail -n 1 gpurun_out/${TAG}_bench.json > profiles/${TAG}_bench_line.json
 [ -f gpurun_out/${TAG}_bench_reference.json ] && tail -n 1 gpurun_out/${TAG}_bench_reference.json > profiles/${TAG}_bench_line_reference.json

@@ -49,17 +49,17 @@ FP32_PEAK_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (BASELINE.md se
 METRIC = "Mpaths/s (Cornell box 600x600, 100 spp per GPU, depth 50)"
 
 # The other BASELINE.json configurations.  `spp`: samples per pixel of one timed step (the config's own
-# count is `full_spp`); `cpu`: the bounded sample the CPU baseline renders (width, spp): the config's own image at BASELINE.md
+# count is `full_spp`); `cpu`: the bounded sample the CPU baseline renders (width, height, spp): the config's own image at BASELINE.md
 # section 3's 16 / 8 / 4 spp, 8 - 25 s of work for the host cores each.
 CONFIGS = [
     dict(name="C2", scene="random_scene", workload="random_scene (main.rs:192-295,816-827: ~485 spheres, 1 in 5 moving, aperture 0.1) 1200x800, depth 50",
-         width=1200, height=800, spp=32, full_spp=500, cpu=(1200, 16)),
+         width=1200, height=800, spp=32, full_spp=500, cpu=(1200, 800, 16)),
     dict(name="C2w", scene="one_weekend", workload="One-Weekend flavour of config 2 (static spheres, fuzz U[0,0.5)) 1200x800, depth 50",
-         width=1200, height=800, spp=32, full_spp=500, cpu=(1200, 16)),
+         width=1200, height=800, spp=32, full_spp=500, cpu=(1200, 800, 16)),
     dict(name="C3", scene="final_scene", workload="final_scene (main.rs:635-795,916-936: 400 boxes, media, Perlin, earth map, 1000-sphere cluster) 800x800, depth 50",
-         width=800, height=800, spp=32, full_spp=10000, cpu=(800, 8)),
+         width=800, height=800, spp=32, full_spp=10000, cpu=(800, 800, 8)),
     dict(name="C5", scene="stress", workload="stress scene (SURVEY.md 8d: 10^6 random spheres + 16 rectangle lights, device-built BVH) 1920x1080, depth 50",
-         width=1920, height=1080, spp=8, full_spp=256, cpu=(1920, 4)),
+         width=1920, height=1080, spp=8, full_spp=256, cpu=(1920, 1080, 4)),
 ]
 # Strong scaling: a FIXED job split over the ranks by the library's shard rule (total spp)
 STRONG = [
@@ -120,10 +120,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_sample(api, oracle_binding, hs, width, spp, aspect=None):
+def cpu_sample(api, oracle_binding, hs, width, spp, aspect=None, height=None):
     """The oracle port on all host cores on a bounded sample of a config: -> cpu_baseline dict."""
     osc = oracle_binding.OracleScene(hs.desc)
-    p = hs.params(width=width, spp=spp)
+    p = hs.params(width=width, height=height, spp=spp)
     _, _, ost = osc.render(hs.camera() if aspect is None else hs.camera(aspect=aspect), p, threads=0)
     osc.close()
     return {"value": ost.paths / ost.seconds / 1e6, "unit": "Mpaths/s", "cores": int(ost.threads), "kind": "port",
@@ -360,7 +360,7 @@ def main():
                                    "upload_ms": round(i.upload_ms, 1)},
                    "roofline": roof}
             if want_cpu:
-                rec["cpu_baseline"] = cpu_sample(api, oracle_binding, h, c["cpu"][0], c["cpu"][1])
+                rec["cpu_baseline"] = cpu_sample(api, oracle_binding, h, c["cpu"][0], c["cpu"][2], height=c["cpu"][1])
                 rec["gpu_over_cpu"] = rec["mpaths_per_s"] / rec["cpu_baseline"]["value"]
             configs.append(rec)
             del buf

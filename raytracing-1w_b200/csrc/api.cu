@@ -193,7 +193,6 @@ struct rt1w_scene {
     // device allocations
     float4 *d_nodes = nullptr;
     uint4 *d_wide_nodes = nullptr;
-    float4 *d_sphere4 = nullptr;
     DPrim *d_prims = nullptr;
     float4 *d_prim_boxes = nullptr;
     int32_t *d_prim_id = nullptr;
@@ -215,7 +214,7 @@ static void scene_release(rt1w_scene *s) {
     cudaSetDevice(s->device);
     for (auto t : s->tex_objects) cudaDestroyTextureObject(t);
     for (auto a : s->arrays) cudaFreeArray(a);
-    cudaFree(s->d_nodes), cudaFree(s->d_wide_nodes), cudaFree(s->d_sphere4), cudaFree(s->d_prims), cudaFree(s->d_prim_boxes), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
+    cudaFree(s->d_nodes), cudaFree(s->d_wide_nodes), cudaFree(s->d_prims), cudaFree(s->d_prim_boxes), cudaFree(s->d_prim_id), cudaFree(s->d_frames), cudaFree(s->d_materials);
     cudaFree(s->d_textures), cudaFree(s->d_perlins), cudaFree(s->d_images), cudaFree(s->d_image_dims), cudaFree(s->d_lights);
     delete s;
 }
@@ -525,12 +524,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
             RT1W_CUDA(cudaMemcpy(bvh.nodes.data(), d_lbvh_nodes, sizeof(BvhNode32) * n_bvh_nodes, cudaMemcpyDeviceToHost));
             cudaFree(d_lbvh_nodes), d_lbvh_nodes = nullptr;
         }
-        // big trees: a leaf slot may hold a small subtree's primitives (up to 4), screened one by one in f32 before the f64 solve -
-        // most of the nodes a ray visits in a big tree are the bottom ones, and a screened group is cheaper than a node
-        // (RT1W_WIDE_LEAF=1..4 overrides: tuning, tests)
-        int wide_leaf = n_bvh_nodes >= size_t(kWideFromNodes) ? 4 : 1;
-        if (const char *env = std::getenv("RT1W_WIDE_LEAF")) wide_leaf = std::atoi(env);
-        collapse_to_bvh8(bvh.nodes.data(), bvh.nodes.size(), wide, wide_leaf, wide_leaf > 1 ? 0.15f : 1.0f);
+        collapse_to_bvh8(bvh.nodes.data(), bvh.nodes.size(), wide);
         if (wide.leaf_remap.size() != nb) return fail(RT1W_ERR_STATE, "wide BVH collapse lost primitives");
         std::vector<uint32_t> new_of_old(nb), order(nb);
         for (size_t i = 0; i < nb; ++i) new_of_old[wide.leaf_remap[i]] = uint32_t(i), order[i] = bvh.prim_order[wide.leaf_remap[i]];
@@ -635,15 +629,6 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
         RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
     }
     if (!wide.nodes.empty() && wide.depth <= kWideMaxDepth) {
-        if (wide.max_leaf_prims > 1) { // f32 (centre, radius) of the plain spheres, for the leaf-slot screen (kernels.cuh: sphere_screen)
-            std::vector<float4> sphere4(n);
-            for (size_t i = 0; i < n; ++i) {
-                const rt1w_flat_prim &fp = dev[bvh.prim_order[i]];
-                const bool plain = fp.kind == RT1W_NODE_SPHERE && fp.frame < 0;
-                sphere4[i] = plain ? make_float4(float(fp.p[0]), float(fp.p[1]), float(fp.p[2]), std::nextafter(float(fp.p[3]), INFINITY)) : make_float4(0.0f, 0.0f, 0.0f, -1.0f);
-            }
-            RT1W_CUDA(upload(sphere4, &s->d_sphere4));
-        }
         static_assert(sizeof(Bvh8Node) == 5 * sizeof(uint4), "wide node layout");
         RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_wide_nodes), sizeof(Bvh8Node) * wide.nodes.size()));
         RT1W_CUDA(cudaMemcpy(s->d_wide_nodes, wide.nodes.data(), sizeof(Bvh8Node) * wide.nodes.size(), cudaMemcpyHostToDevice));
@@ -693,7 +678,6 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
     v.n_global = int32_t(n_global);
     v.n_prims = int32_t(n), v.n_nodes = int32_t(n_bvh_nodes), v.n_perlins = int32_t(low.perlins.size()), v.n_frames = int32_t(low.frames.size());
     v.flat = flat ? 1 : 0;
-    v.sphere4 = s->d_sphere4;
     v.wide_nodes = s->d_wide_nodes, v.n_wide = s->d_wide_nodes ? int32_t(wide.nodes.size()) : 0;
     v.wide = !flat && n_bvh_nodes >= size_t(kWideFromNodes) ? 1 : 0;
     if (const char *env = std::getenv("RT1W_BVH_LAYOUT")) // binary | wide: overrides the size rule (tuning, tests)

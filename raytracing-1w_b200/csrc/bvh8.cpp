@@ -25,18 +25,13 @@ struct Work {
 // children (i = 1: ONE child - the primitive itself for a leaf, else a wide node whose own up-to-8 children come out of
 // n's two subtrees); a wide node costs its area (one fetch + eight box tests per visit), a leaf slot its area (one f64
 // solve per visit).  split[n][i - 1]: how many of the i come from the left subtree (0: "i - 1 were enough").
-// A subtree of at most max_leaf_prims primitives may also become ONE leaf slot (its box = the subtree's): the traversal then
-// screens its primitives one by one (kernels.cuh: trav_step_leaf) instead of fetching and testing one more node; such a
-// slot costs area * primitives * leaf_cost (leaf_cost: a primitive screen relative to a node visit).
 struct Plan {
     std::vector<float> cost;    // 7 per node
     std::vector<uint8_t> split; // 8 per node: [0..6] for i = 1..7 (unused for i = 1), [7] for the node's own 8 children
-    std::vector<uint8_t> leafy; // the subtree as ONE child is a leaf slot holding all its primitives
-    std::vector<uint32_t> prims; // primitives under the node
 };
 
-void plan_collapse(const BvhNode32 *nodes, size_t n_nodes, int max_leaf_prims, float leaf_cost, Plan &plan) {
-    plan.cost.assign(7 * n_nodes, 0.0f), plan.split.assign(8 * n_nodes, 0), plan.leafy.assign(n_nodes, 0), plan.prims.assign(n_nodes, 0);
+void plan_collapse(const BvhNode32 *nodes, size_t n_nodes, Plan &plan) {
+    plan.cost.assign(7 * n_nodes, 0.0f), plan.split.assign(8 * n_nodes, 0);
     // post-order without recursion: children before parents
     std::vector<uint32_t> order, stack;
     order.reserve(n_nodes), stack.push_back(0u);
@@ -52,11 +47,9 @@ void plan_collapse(const BvhNode32 *nodes, size_t n_nodes, int max_leaf_prims, f
         float *c = &plan.cost[7 * size_t(n)];
         uint8_t *sp = &plan.split[8 * size_t(n)];
         if (nodes[n].count != 0) {
-            for (int i = 0; i < 7; ++i) c[i] = area * leaf_cost;
-            plan.leafy[n] = 1, plan.prims[n] = 1;
+            for (int i = 0; i < 7; ++i) c[i] = area;
             continue;
         }
-        plan.prims[n] = plan.prims[nodes[n].left_first] + plan.prims[nodes[n].left_first + 1];
         const float *cl = &plan.cost[7 * size_t(nodes[n].left_first)], *cr = cl + 7;
         auto distribute = [&](int j, uint8_t &best_k) { // j >= 2 children out of the two subtrees
             float best = INFINITY;
@@ -67,9 +60,7 @@ void plan_collapse(const BvhNode32 *nodes, size_t n_nodes, int max_leaf_prims, f
             }
             return best;
         };
-        c[0] = distribute(8, sp[7]) + area; // n itself becomes a wide node ...
-        if (plan.prims[n] <= uint32_t(max_leaf_prims) && area * leaf_cost * float(plan.prims[n]) <= c[0])
-            c[0] = area * leaf_cost * float(plan.prims[n]), plan.leafy[n] = 1; // ... or one leaf slot
+        c[0] = distribute(8, sp[7]) + area; // n itself becomes a wide node
         for (int i = 2; i <= 7; ++i) {
             uint8_t kk = 0;
             const float d = distribute(i, kk);
@@ -93,12 +84,11 @@ void collect_children(const BvhNode32 *nodes, const Plan &plan, uint32_t n, int 
 
 } // namespace
 
-void collapse_to_bvh8(const BvhNode32 *nodes, size_t n_nodes, Bvh8BuildResult &out, int max_leaf_prims, float leaf_cost) {
+void collapse_to_bvh8(const BvhNode32 *nodes, size_t n_nodes, Bvh8BuildResult &out) {
     out.nodes.clear(), out.leaf_remap.clear(), out.depth = 0, out.avg_children = 0.0;
     if (n_nodes == 0) return;
-    max_leaf_prims = std::min(std::max(max_leaf_prims, 1), 4); // (the node keeps primitives - 1 of a leaf slot in two bits)
     Plan plan;
-    plan_collapse(nodes, n_nodes, max_leaf_prims, leaf_cost, plan);
+    plan_collapse(nodes, n_nodes, plan);
     out.nodes.reserve(n_nodes / 5 + 16);
     out.leaf_remap.reserve(n_nodes / 2 + 1);
     std::vector<Work> queue;
@@ -113,7 +103,7 @@ void collapse_to_bvh8(const BvhNode32 *nodes, size_t n_nodes, Bvh8BuildResult &o
         uint32_t kids[8];
         int n_kids = 0;
         const BvhNode32 &top = nodes[w.binary];
-        if (top.count != 0 || (w.wide == 0 && plan.leafy[w.binary])) { // a tree that is one leaf slot
+        if (top.count != 0) { // a single-leaf tree
             kids[n_kids++] = w.binary;
         } else {
             const int k = plan.split[8 * size_t(w.binary) + 7];
@@ -178,21 +168,13 @@ void collapse_to_bvh8(const BvhNode32 *nodes, size_t n_nodes, Bvh8BuildResult &o
                 node.qlo[a][s] = uint8_t(std::min(std::max(ql, 0.0), 255.0));
                 node.qhi[a][s] = uint8_t(std::min(std::max(qh, 0.0), 255.0));
             }
-            if (c.count == 0 && !plan.leafy[kids[k]]) {
+            if (c.count == 0) {
                 node.imask |= uint8_t(1u << s);
                 queue.push_back(Work{kids[k], uint32_t(out.nodes.size()), w.depth + 1});
                 out.nodes.push_back(Bvh8Node{});
-            } else { // a leaf slot: the primitives under the binary node, depth first
-                uint32_t held = 0, todo[16];
-                int n_todo = 0;
-                todo[n_todo++] = kids[k];
-                while (n_todo > 0) {
-                    const BvhNode32 &b = nodes[todo[--n_todo]];
-                    if (b.count != 0) out.leaf_remap.push_back(b.left_first), ++held;
-                    else todo[n_todo++] = b.left_first + 1, todo[n_todo++] = b.left_first;
-                }
-                node.leaf_mask |= (1u << s) | ((held - 1u) << (8 + 2 * s));
-                out.max_leaf_prims = std::max(out.max_leaf_prims, int(held));
+            } else {
+                node.leaf_mask |= 1u << s;
+                out.leaf_remap.push_back(c.left_first);
             }
         }
         out.nodes[w.wide] = node;

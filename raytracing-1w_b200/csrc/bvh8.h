@@ -13,7 +13,7 @@
 //           and `imask` (bit s set: slot s holds an INTERIOR child)
 //   word 1  child_base (node index of the first interior child; the interior children of a node are adjacent, in slot
 //           order), prim_base (leaf index of the first leaf slot's primitive; likewise adjacent, in slot order),
-//           leaf word (bits 0-7: slot s is a LEAF slot; bits 8 + 2 s, 9 + 2 s: its primitives - 1, i.e. 1 .. 4 of them), unused
+//           leaf_mask (bit s set: slot s holds ONE primitive), unused
 //   words 2-4  child boxes on the grid, one byte per plane: lo.x[8], lo.y[8], lo.z[8], hi.x[8], hi.y[8], hi.z[8]
 //           (lo rounded down, hi rounded up: the decoded box contains the child's conservative f32 box; an empty
 //           slot holds lo = 255, hi = 0)
@@ -46,15 +46,12 @@ struct Bvh8BuildResult {
     std::vector<Bvh8Node> nodes;      // node 0 = root
     std::vector<uint32_t> leaf_remap; // new leaf index -> leaf index of the binary tree it was collapsed from
     int depth = 0;                    // deepest node (root = 0)
-    int max_leaf_prims = 0;           // most primitives any leaf slot holds
     double avg_children = 0.0;        // occupied slots per node
 };
 
 // Collapses a binary tree in the layout of bvh.h (single-primitive leaves, node 0 = root, siblings adjacent) into the wide
 // tree: a node's children are found by opening, largest surface area first, interior children of the binary subtree
 // until eight are in hand.  `nodes` may come from either builder (host SAH, device LBVH).
-// max_leaf_prims (1 .. 4): a leaf slot may hold that many primitives (a whole small subtree); leaf_cost: what screening one
-// of them costs relative to visiting a node (the dynamic programme weighs the two).
-void collapse_to_bvh8(const BvhNode32 *nodes, size_t n_nodes, Bvh8BuildResult &out, int max_leaf_prims = 1, float leaf_cost = 1.0f);
+void collapse_to_bvh8(const BvhNode32 *nodes, size_t n_nodes, Bvh8BuildResult &out);
 
 } // namespace rt1w

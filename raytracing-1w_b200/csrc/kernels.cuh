@@ -35,7 +35,6 @@ constexpr int kStackLocal = 64 - RT1W_STACK_SMEM; // overflow entries (local mem
 struct SceneView {
     const float4 *nodes;       // 2 x float4 per node
     const uint4 *wide_nodes;   // 5 x uint4 per node of the compressed 8-wide tree (bvh8.h), or nullptr
-    const float4 *sphere4;     // wide tree with multi-primitive leaf slots: per leaf (centre, radius) of a plain sphere in f32, radius <= 0 for anything else
     const DPrim *prims;        // leaf order
     const float4 *prim_boxes;  // flat scenes: 3 x float4 per primitive in SCAN order (see flat_stage), else nullptr
     const int32_t *prim_id;    // leaf index -> primitive id (DFS order of the description)
@@ -506,7 +505,7 @@ struct TravW {
     float bestf;   // its f32 upper bound (with the slack of `slab`), for the node tests
     int best_leaf; // leaf | side << kLeafBits, or -1
     uint2 ng;      // interior children still to visit: x = child_base, y = pending slots (bits 8..15) | imask (bits 0..7)
-    uint2 lg;      // leaf slots the last node test hit: x = prim_base, y = pending slots (bits 24..31) | the node's leaf word (bvh8.h: mask, primitives - 1 per slot)
+    uint2 lg;      // leaf slots the last node test hit: x = prim_base, y = pending slots (bits 8..15) | leaf_mask
     uint32_t oct;  // bit k set: direction component k >= 0
     int sp;
 };
@@ -529,9 +528,9 @@ RT1W_DEV uint32_t octant_order(uint32_t m, uint32_t oct) {
 RT1W_DEV uint32_t next_slot(uint32_t y, uint32_t oct) { return (31u - uint32_t(__clz(int(octant_order(y >> 8, oct))))) ^ oct; }
 
 RT1W_DEV void trav_reset(TravW &T) { T.ng = make_uint2(0u, 0u), T.lg = make_uint2(0u, 0u), T.sp = 0; }
-RT1W_DEV bool trav_at_leaf(const TravW &T) { return (T.lg.y >> 24) != 0u; }
-RT1W_DEV bool trav_interior(const TravW &T) { return (T.lg.y >> 24) == 0u && ((T.ng.y >> 8) != 0u || T.sp > 0); }
-RT1W_DEV bool trav_done(const TravW &T) { return (T.lg.y >> 24) == 0u && (T.ng.y >> 8) == 0u && T.sp <= 0; }
+RT1W_DEV bool trav_at_leaf(const TravW &T) { return (T.lg.y >> 8) != 0u; }
+RT1W_DEV bool trav_interior(const TravW &T) { return (T.lg.y >> 8) == 0u && ((T.ng.y >> 8) != 0u || T.sp > 0); }
+RT1W_DEV bool trav_done(const TravW &T) { return (T.lg.y >> 8) == 0u && (T.ng.y >> 8) == 0u && T.sp <= 0; }
 
 constexpr float kBestSlack = 1.000001f; // the f32 node tests against the f64 solve's best hit: rcp.approx scales every plane distance by up to 2^-23
 RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, TravW &T) {
@@ -588,9 +587,9 @@ RT1W_DEV void wide_visit(const SceneView &sc, uint32_t node, TravW &T) {
     }
     RT1W_WIDE_SLOT(0) RT1W_WIDE_SLOT(1) RT1W_WIDE_SLOT(2) RT1W_WIDE_SLOT(3) RT1W_WIDE_SLOT(4) RT1W_WIDE_SLOT(5) RT1W_WIDE_SLOT(6) RT1W_WIDE_SLOT(7)
 #undef RT1W_WIDE_SLOT
-    const uint32_t imask = em >> 24, lword = w1.z & 0xffffffu; // empty slots are in neither mask
+    const uint32_t imask = em >> 24, lmask = w1.z & 0xffu; // empty slots are in neither
     T.ng = make_uint2(w1.x, ((hits & imask) << 8) | imask);
-    T.lg = make_uint2(w1.y, ((hits & lword & 0xffu) << 24) | lword);
+    T.lg = make_uint2(w1.y, ((hits & lmask) << 8) | lmask);
 }
 
 // the nearest pending interior child (of this node, else of the most recent node with children left)
@@ -607,43 +606,24 @@ RT1W_DEV void trav_step_interior(const SceneView &sc, TravW &T, uint2 *stack, in
     wide_visit(sc, node, T);
 }
 
-// f32 screen of a plain sphere in a leaf slot that holds several primitives (its box is the whole group's): false only when
-// the ray's LINE certainly passes the sphere by.  The distance of the centre from the line is taken from the closest point
-// (no r^2 - |oc|^2 cancellation), the centre relative to the f64 origin; the margin covers the f32 rounding of both.
-RT1W_DEV bool sphere_screen(const float4 sp, const Ray &r) {
-    const f3 oc = mk3(float(double(sp.x) - r.ox), float(double(sp.y) - r.oy), float(double(sp.z) - r.oz)), d = mk3(r.dx, r.dy, r.dz);
-    const float tc = dot(oc, d) / dot(d, d), oc2 = dot(oc, oc);
-    const f3 q = mk3(fmaf(-tc, d.x, oc.x), fmaf(-tc, d.y, oc.y), fmaf(-tc, d.z, oc.z));
-    const float reach = sp.w + 2e-6f * sqrtf(oc2) + 2e-7f * (fabsf(sp.x) + fabsf(sp.y) + fabsf(sp.z));
-    return dot(q, q) <= reach * reach;
-}
-
-// the leaf slots the last node test hit, nearest first: f64 solves (a slot holding several primitives screens its spheres first)
+// the leaf slots the last node test hit, nearest first: f64 solves
 template <bool EXACT, bool MEDIA>
 RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng &mr, TravW &T, const uint2 *, int, const uint2 *) {
-    const uint32_t lmask = T.lg.y & 0xffu, more = (T.lg.y >> 8) & 0xffffu; // primitives - 1 per slot, two bits each
-    while ((T.lg.y >> 24) != 0u) {
-        const uint32_t slot = (31u - uint32_t(__clz(int(octant_order(T.lg.y >> 24, T.oct))))) ^ T.oct;
-        T.lg.y &= ~(0x1000000u << slot);
-        const uint32_t below = more & ((1u << (2u * slot)) - 1u); // the slots before this one: one primitive each + their extras
-        const int first = int(T.lg.x + uint32_t(__popc(lmask & ((1u << slot) - 1u))) + uint32_t(__popc(below & 0x5555u)) + 2u * uint32_t(__popc(below & 0xaaaau)));
-        const int count = 1 + int((more >> (2u * slot)) & 3u);
-        for (int leaf = first; leaf < first + count; ++leaf) {
-            if (count > 1) {
-                const float4 sp = __ldg(sc.sphere4 + leaf);
-                if (sp.w > 0.0f && !sphere_screen(sp, r)) continue;
+    const uint32_t lmask = T.lg.y & 0xffu;
+    while ((T.lg.y >> 8) != 0u) {
+        const uint32_t slot = next_slot(T.lg.y, T.oct);
+        T.lg.y &= ~(0x100u << slot);
+        const int leaf = int(T.lg.x + uint32_t(__popc(lmask & ((1u << slot) - 1u))));
+        uint32_t box_sides = 0u;
+        do {
+            double t;
+            int side = 0;
+            RT1W_TRAV_COUNT(2);
+            if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + leaf, leaf, r, T.best, mr, t, box_sides, side)) {
+                T.best = t, T.best_leaf = leaf | (side << kLeafBits);
+                T.bestf = __double2float_ru(t) * kBestSlack;
             }
-            uint32_t box_sides = 0u;
-            do {
-                double t;
-                int side = 0;
-                RT1W_TRAV_COUNT(2);
-                if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + leaf, leaf, r, T.best, mr, t, box_sides, side)) {
-                    T.best = t, T.best_leaf = leaf | (side << kLeafBits);
-                    T.bestf = __double2float_ru(t) * kBestSlack;
-                }
-            } while (box_sides != 0u);
-        }
+        } while (box_sides != 0u);
     }
 }
 

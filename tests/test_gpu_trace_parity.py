@@ -12,17 +12,17 @@ from common import check_trace_parity, make_ray_set
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # scene, rays (SURVEY.md 8d asks for 2^20; the oracle's median-split trees answer the bigger scenes more slowly),
-    # sampling box half-size around look_at (None = scene bounds), aspect handed to Camera::new (None = the scene's own)
+    # scene, rays (N = 2^20 per scene), sampling box half-size around look_at (None = scene bounds),
+    # aspect handed to Camera::new (None = the scene's own)
     ("cornel_box", 1 << 20, None, None),
     ("cornel_box", 1 << 18, None, 3840.0 / 2160.0),  # BASELINE config 4: the 16:9 camera sees past the room
-    ("cornel_smoke", 1 << 17, None, None),
-    ("simple_light", 1 << 16, 30.0, None),
-    ("two_spheres", 1 << 16, 30.0, None),
-    ("random_scene", 1 << 17, 15.0, None),
-    ("one_weekend", 1 << 17, 15.0, None),  # BASELINE config 2 in its One-Weekend flavour (static spheres)
-    ("final_scene", 1 << 17, 700.0, None),
-    ("earth", 1 << 15, 10.0, None),
+    ("cornel_smoke", 1 << 20, None, None),
+    ("simple_light", 1 << 20, 30.0, None),
+    ("two_spheres", 1 << 20, 30.0, None),
+    ("random_scene", 1 << 20, 15.0, None),
+    ("one_weekend", 1 << 20, 15.0, None),  # BASELINE config 2 in its One-Weekend flavour (static spheres)
+    ("final_scene", 1 << 20, 700.0, None),
+    ("earth", 1 << 20, 10.0, None),
 ]
 
 

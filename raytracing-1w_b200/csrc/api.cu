@@ -905,8 +905,9 @@ rt1w_status rt1w_render(rt1w_scene *scene, const rt1w_camera *camera, const rt1w
     RT1W_CUDA(cudaSetDevice(ctx->device));
     if (params->width <= 0 || params->height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
     const size_t pixels = size_t(params->width) * size_t(params->height);
-    const bool want_stat = (params->flags & RT1W_FLAG_STATS) != 0 && (out_stat != nullptr || !root);
-    if (out_stat && !(params->flags & RT1W_FLAG_STATS)) return fail(RT1W_ERR_INVALID, "out_stat needs RT1W_FLAG_STATS");
+    // (the flag alone decides whether the statistics buffers exist: in a communicator every rank must join the same reduces)
+    const bool want_stat = (params->flags & RT1W_FLAG_STATS) != 0;
+    if (out_stat && !want_stat) return fail(RT1W_ERR_INVALID, "out_stat needs RT1W_FLAG_STATS");
     rt1w_status st = ensure_buffers(ctx, pixels, want_stat, false);
     if (st != RT1W_OK) return st;
     st = render_dispatch(scene, camera, params, ctx->d_accum, want_stat ? ctx->d_stat : nullptr, ctx->stream, stats);

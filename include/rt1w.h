@@ -166,6 +166,9 @@ typedef struct rt1w_camera {
 /* BVH scenes: which tree is walked (default: by BVH size).  Same leaves, same conservative boxes, same closest hits. */
 #define RT1W_FLAG_BVH_BINARY 16u /* 32-byte nodes, two children per step */
 #define RT1W_FLAG_BVH_WIDE 32u   /* compressed 8-wide nodes (80 bytes, eight quantised child boxes per step) */
+/* Waves to the very end: without it, once about one hit per resident thread is left, one kernel follows every remaining path
+ * to its end inside a thread (same scatter, same closest hit, same random numbers: same image). A/B measurements, tests. */
+#define RT1W_FLAG_NO_TAIL 64u
 
 /* kernel slots of rt1w_render_stats.kernel_ms / kernel_launches */
 #define RT1W_KERNEL_WAVE 0  /* k_wave / k_wave_bvh: scatter queued hits / start camera paths, closest hit, regroup per material */

@@ -22,6 +22,7 @@ FLAG_BVH_LOCKSTEP = 4
 FLAG_BVH_PERSISTENT = 8
 FLAG_BVH_BINARY = 16
 FLAG_BVH_WIDE = 32
+FLAG_NO_TAIL = 64
 
 SCENE_IDS = {"random_scene": 0, "two_spheres": 1, "two_perlin_spheres": 2, "earth": 3, "simple_light": 4,
              "cornel_box": 5, "cornel_smoke": 6, "final_scene": 7, "stress": 8, "one_weekend": 9}

@@ -441,6 +441,112 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
 }
 
 // ------------------------------------------------------------------------------------------
+// the end of a render: the last paths run to completion, one thread each
+// ------------------------------------------------------------------------------------------
+// Depth 50 and no Russian roulette (main.rs:59-61): after the last path has started, the rays in flight shrink by a
+// fifth per bounce, and the last ~45 of a Cornell render's ~72 waves hold less than one ray per resident thread - each of
+// them still costs the latency of one trip through scatter + closest hit (~10 us), a barrier per bounce.  Once the
+// queues hold few enough hits (max_items: about a ray per resident thread), this kernel - launched after every chunk of
+// waves, a no-op until then - takes every queued hit and follows its path bounce after bounce inside ONE thread until it
+// ends: no barrier between bounces, the warp diverges over materials and depths instead.  Same scatter, same closest hit,
+// same Philox counters as the waves: the image does not depend on when (or whether) it takes over.
+// The last CTA to finish zeroes the queue counters it consumed, so the waves launched after it find nothing to do.
+template <bool FLAT, bool MEDIA, bool RICH>
+__global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLAT, MEDIA))
+    k_tail(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem, const uint32_t max_items) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    constexpr int kThreads = wave_threads(FLAT, MEDIA);
+    constexpr size_t kFlatBytes = sizeof(FlatScene) + sizeof(float) * kFlatMax * kThreads;
+    __shared__ __align__(16) unsigned char s_raw[FLAT ? kFlatBytes : sizeof(uint2) * kStackSmem * kWaveThreads];
+    __shared__ DLight s_lights[RT1W_MAX_LIGHTS];
+    __shared__ unsigned int s_traced;
+    uint2 *s_stack = reinterpret_cast<uint2 *>(s_raw);
+    FlatScene *s_flat = reinterpret_cast<FlatScene *>(s_raw);
+    float *s_tn = reinterpret_cast<float *>(s_raw + sizeof(FlatScene));
+
+    Counters *ctr = a.pool.ctr;
+    const uint32_t cnt0 = ctr->n_mat[slot][scatter_mat(0)], cnt1 = ctr->n_mat[slot][scatter_mat(1)];
+    const uint32_t cnt2 = ctr->n_mat[slot][scatter_mat(2)], cnt3 = ctr->n_mat[slot][scatter_mat(3)];
+    const uint32_t queued = cnt0 + cnt1 + cnt2 + cnt3;
+    if (queued == 0u || queued > max_items || ctr->next_path[slot] < a.rp.total_paths) return; // not yet (or nothing left): every CTA decides alike
+    const uint32_t off1 = (cnt0 + 31u) & ~31u, off2 = off1 + ((cnt1 + 31u) & ~31u), off3 = off2 + ((cnt2 + 31u) & ~31u);
+    const uint32_t off4 = off3 + ((cnt3 + 31u) & ~31u);
+
+    if (FLAT) flat_stage(a.sc, s_flat[0]);
+    const DPerlin *perlins = a.sc.perlins;
+    if (RICH && perlin_in_smem) {
+        const uint32_t words = uint32_t(a.sc.n_perlins) * uint32_t(sizeof(DPerlin) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sc.perlins);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_dyn);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+        perlins = reinterpret_cast<const DPerlin *>(s_dyn);
+    }
+    for (int l = threadIdx.x; l < a.sc.n_lights; l += blockDim.x) s_lights[l] = a.sc.lights[l];
+    if (threadIdx.x == 0) s_traced = 0;
+    __syncthreads();
+    const DPrim *prims = FLAT ? s_flat[0].prims : a.sc.prims;
+    const DFrame *frames = FLAT ? s_flat[0].frames : a.sc.frames;
+
+    uint32_t traced = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < off4; i += gridDim.x * blockDim.x) {
+        const int seg = i < off1 ? 0 : (i < off2 ? 1 : (i < off3 ? 2 : 3));
+        const uint32_t j = i - (seg == 0 ? 0u : (seg == 1 ? off1 : (seg == 2 ? off2 : off3)));
+        if (j >= (seg == 0 ? cnt0 : (seg == 1 ? cnt1 : (seg == 2 ? cnt2 : cnt3)))) continue;
+        const RayQueue &in = a.pool.mat[parity][scatter_mat(seg)];
+        RayC c;
+        Ray r = load_ray(in, j, c);
+        HitRec hr = stream_load(in.h + j);
+        const float4 th4 = stream_load(in.t + j);
+        f3 thr = mk3(th4.x, th4.y, th4.z);
+        int mat = scatter_mat(seg);
+        for (;;) { // one bounce per trip: scatter at the hit, closest hit of the scattered ray
+            if (!scatter<MEDIA, RICH>(mat, a, prims, frames, perlins, s_lights, r, hr, c, thr)) { // depth limit: zero radiance
+                if (!finite3(thr)) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
+                break;
+            }
+            ++traced;
+            MediumRng mr = {0, 0, 0, 0, 0};
+            if (MEDIA) {
+                path_rng_key(a.rp, c.pixel, mr.k0, mr.k1);
+                mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
+            }
+            HitRec h;
+            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kThreads, hr.leaf, h.t, h.leaf)
+                                  : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
+            int mat_type = RT1W_MAT_NONE;
+            if (hit) {
+                h.meta = FLAT ? s_flat[0].prims[h.leaf & kLeafMask].meta : __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
+                mat_type = int((h.meta >> 8) & 15u);
+            }
+            if (mat_type == RT1W_MAT_DIFFUSE_LIGHT || mat_type == RT1W_MAT_NONE) { // main.rs:110-115: the path ends here
+                f3 rad = mk3(0.0f, 0.0f, 0.0f);
+                if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) {
+                    const HitInfo hi = finalize_hit<false>(prims + (h.leaf & kLeafMask), frames, h.leaf >> kLeafBits, r, h.t);
+                    if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
+                } else if (!hit) {
+                    rad = mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
+                }
+                if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f || !finite3(thr)) splat(a, c.pixel, thr, rad);
+                break;
+            }
+            hr = h, mat = mat_type;
+        }
+    }
+    traced = __reduce_add_sync(0xffffffffu, traced);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(&s_traced, traced);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_traced) atomicAdd(&ctr->rays, (unsigned long long)s_traced);
+        __threadfence();
+        if (atomicAdd(&ctr->tail_ticket, 1u) == gridDim.x - 1u) { // the last CTA: every CTA has read the counters it is about to close
+#pragma unroll
+            for (int q = 0; q < Q_COUNT; ++q) ctr->n_mat[slot][q] = 0;
+            ctr->tail_done = 1u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // the wave kernel of BVH scenes: persistent warps, rays replaced lane by lane
 // ------------------------------------------------------------------------------------------
 // BVH traversal lengths vary wildly from ray to ray (a 1 M-sphere scene: 5 of 32 lanes busy when a warp
@@ -956,10 +1062,27 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
             if (!l2_window) cudaGetLastError();
         }
     }
+    // the kernel that runs the last paths to completion (k_tail); RT1W_FLAG_NO_TAIL keeps waves to the end (A/B, tests)
+    using TailKernel = void (*)(const RenderArgs, const int, const int, const int, const uint32_t);
+    TailKernel tail_kernel = nullptr;
+    if (!persistent && !wide && !(args.rp.flags & RT1W_FLAG_NO_TAIL))
+        tail_kernel = flat ? (media ? (rich ? k_tail<true, true, true> : k_tail<true, true, false>) : (rich ? k_tail<true, false, true> : k_tail<true, false, false>))
+                           : (media ? (rich ? k_tail<false, true, true> : k_tail<false, true, false>) : (rich ? k_tail<false, false, true> : k_tail<false, false, false>));
+    if (tail_kernel && flat) cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int threads = wave_threads(flat, media);
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
     const int blocks = sm_count * (per_sm > 0 ? per_sm : 1);
+    const uint32_t tail_items = uint32_t(blocks) * uint32_t(threads); // one queued hit per resident thread
+    if (tail_kernel && perlin_bytes > 0) { // the same shared-memory opt-in as the wave kernel's (or no tail kernel)
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, tail_kernel) != cudaSuccess ||
+            (fa.sharedSizeBytes + perlin_bytes > 48 * 1024 &&
+             cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(perlin_bytes)) != cudaSuccess)) {
+            cudaGetLastError();
+            tail_kernel = nullptr;
+        }
+    }
     // every wave may start (scene tables -> shared memory) while the wave before it drains: programmatic dependent launch
     cudaLaunchAttribute launch_attr[1];
     launch_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1018,6 +1141,13 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
                 continue;
             }
             if ((e = cudaLaunchKernelEx(&launch, kernel, args, slot, parity, perlin_in_smem)) != cudaSuccess) break;
+            ++ws.launches;
+        }
+        if (tail_kernel && e == cudaSuccess) { // a no-op until few enough hits are queued, then the rest of the render (k_tail)
+            cudaLaunchConfig_t cfg = launch;
+            cfg.attrs = nullptr, cfg.numAttrs = 0;
+            mark(K_WAVE);
+            if ((e = cudaLaunchKernelEx(&cfg, tail_kernel, args, int(wave % 3), int(wave & 1), perlin_in_smem, tail_items)) != cudaSuccess) break;
             ++ws.launches;
         }
         mark(-1);

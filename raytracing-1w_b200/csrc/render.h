@@ -17,6 +17,8 @@ struct Counters {
     uint32_t split_total;            // split-pipeline A/B only (render.cu: k_wave<.., PHASE>): work items the shade launch left for the extend launch
     unsigned long long next_path[3]; // next (pixel, sample) pair to start, as seen by the wave that reads the slot
     unsigned long long rays;         // closest-hit queries so far
+    uint32_t tail_ticket;            // k_tail: CTAs that have finished (the last one closes the queues)
+    uint32_t tail_done;              // k_tail has run the remaining paths to their ends
 };
 
 // One queue = SoA payload arrays; entry i of every array belongs to the same ray, so a warp reading

@@ -113,3 +113,21 @@ def test_bvh_wave_kernels_agree(rt, gpu_ctx, name):
     b1 = gsc.render(cam, hs.params(width=96, spp=16, seed=5, flags=api.FLAG_BVH_PERSISTENT, max_depth=3))
     assert a1[2].rays == b1[2].rays
     gsc.close()
+
+
+@pytest.mark.parametrize("name,width,spp", [("cornel_box", 128, 16), ("cornel_smoke", 96, 16), ("random_scene", 128, 8), ("final_scene", 64, 8)])
+def test_tail_kernel_changes_nothing(rt, gpu_ctx, name, width, spp):
+    """The end of a render - once about one hit per resident thread is queued, ONE kernel follows every remaining path to
+    its end inside a thread (render.cu: k_tail) instead of ~45 sparse waves - is the same computation: same scatter, same
+    closest hit, same Philox counters.  With `RT1W_FLAG_NO_TAIL` (waves to the end) the same image, in fewer launches."""
+    api = rt.api
+    hs = api.HostScene(name, seed=1)
+    gsc = api.Scene(gpu_ctx, hs.desc)
+    cam = hs.camera()
+    a = gsc.render(cam, hs.params(width=width, spp=spp, seed=7))
+    b = gsc.render(cam, hs.params(width=width, spp=spp, seed=7, flags=api.FLAG_NO_TAIL))
+    check_same_render(a, b, name)
+    assert a[2].waves < b[2].waves  # the tail kernel took over before depth 50
+    c = gsc.render(cam, hs.params(width=width, spp=spp, seed=7, pool_paths=4096))  # many small waves, the tail kernel right away
+    check_same_render(a, c, name + ", small pool")
+    gsc.close()

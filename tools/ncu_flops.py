@@ -59,6 +59,7 @@ def full_capture(path):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
     out = {}
     for c in CONFIGS:
         base = os.path.join(ROOT, "gpurun_out", f"{tag}_{c}")
@@ -79,7 +80,7 @@ def main():
                "thread_instructions_per_ray": sums.get("smsp__thread_inst_executed.sum", 0.0) / rays, "rays_per_path": perf["rays_per_path"]}
         rec.update(full_capture(base + "_wave.ncu-rep"))
         out[c] = rec
-    with open(os.path.join(ROOT, "profiles", f"{tag}_flops.json"), "w") as f:
+    with open(os.path.join(out_dir, f"{tag}_flops.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out, indent=1))
 

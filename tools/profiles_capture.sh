@@ -1,8 +1,9 @@
 #!/bin/bash
 # Round-end rehearsal on one GPU + the captures behind profiles/<TAG>_*: smoke, the GPU tests, both bench arms as the driver runs
 # them, the launch list of the bench command, one `ncu --set full` capture of a steady-state wave per BASELINE config, and
-# ncu-counted flops of one whole render per config.  Afterwards, here: tools/profiles_refresh.sh <TAG> (summaries, regions,
-# metrics, profiles/<TAG>_flops.json) and tools/ab_split.sh for the fused-vs-split A/B.
+# ncu-counted flops of one whole render per config, digested on the box by tools/profiles_refresh.sh into
+# gpurun_out/profiles_<TAG>/ (summaries, regions, metrics, <TAG>_flops.json).  Afterwards, here:
+#     cp gpurun_out/profiles_r02/* profiles/        (and tools/ab_split.sh for the fused-vs-split A/B)
 #     gpurun --timeout 2400 -- 'bash tools/profiles_capture.sh r02'
 TAG=${1:-r02}
 mkdir -p gpurun_out
@@ -19,4 +20,7 @@ for spec in C1:cornel_box:100:3 C2:random_scene:32:2 C2w:one_weekend:32:2 C3:fin
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_wave -s $skip -c 1 -f -o gpurun_out/${TAG}_${name}_wave python tools/scene_perf.py $scene:$spp > gpurun_out/${TAG}_${name}_full.log 2>&1
   timeout 900 ncu --metrics $M --clock-control none -k regex:k_wave -c 400 --csv --log-file gpurun_out/${TAG}_${name}_flops.csv python tools/scene_perf.py $scene:$spp > gpurun_out/${TAG}_${name}_flops.json 2> gpurun_out/${TAG}_${name}_flops.err
 done
-ls -la gpurun_out | grep ${TAG}_ | head -40
+# digest here (the .ncu-rep files are ~10 MB each: more than gpurun brings back), then drop them
+bash tools/profiles_refresh.sh ${TAG} gpurun_out/profiles_${TAG} > /dev/null 2>&1
+rm -f gpurun_out/${TAG}_*_wave.ncu-rep gpurun_out/${TAG}_*_flops.csv
+ls -la gpurun_out/profiles_${TAG} | head -40

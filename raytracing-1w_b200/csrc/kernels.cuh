@@ -274,6 +274,7 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
     if (type == P_XY_RECT || type == P_XZ_RECT || type == P_YZ_RECT || (BOXES && type == P_BOX)) { // one rectangle test
         int ax = P_YZ_RECT - type;
         double a0 = p01.x, a1 = p01.y, b0 = p23.x, b1 = p23.y, k = w[2].x;
+        bool box_first = false;
         if (BOXES && type == P_BOX) {
             const double2 q01 = w[2];
             const double x0 = p01.x, y0 = p01.y, z0 = p23.x, x1 = q01.x, y1 = q01.y, z1 = __hiloint2double(tail.y, tail.x);
@@ -294,30 +295,44 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
             k = ax == 0 ? (low_plane ? x0 : x1) : (ax == 1 ? (low_plane ? y0 : y1) : (low_plane ? z0 : z1));
             a0 = ax == 0 ? y0 : x0, a1 = ax == 0 ? y1 : x1;
             b0 = ax == 2 ? y0 : z0, b1 = ax == 2 ? y1 : z1;
-            const bool hit = hit_rect(l, ax, a0, a1, b0, b1, k, kTMin, tmax, t);
-            if (first && hit) box_sides = 0u; // the side f32 named was right: nothing closer on this box
-            if ((box_sides & 0x3fu) == 0u) box_sides = 0u;
-            return hit;
+            box_first = first;
         }
-        return hit_rect(l, ax, a0, a1, b0, b1, k, kTMin, tmax, t);
+        // ONE call site for plain rectangles and box sides, ONE sphere solve for the three sphere kinds below: lanes on
+        // different primitive kinds share the instruction stream, and the kernel's hot code stays near the 32 KB the
+        // instruction cache holds
+        const bool hit = hit_rect(l, ax, a0, a1, b0, b1, k, kTMin, tmax, t);
+        if (BOXES && type == P_BOX) {
+            if (box_first && hit) box_sides = 0u; // the side f32 named was right: nothing closer on this box
+            if ((box_sides & 0x3fu) == 0u) box_sides = 0u;
+        }
+        return hit;
     }
-    switch (type) {
-    case P_SPHERE: return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
-    case P_MOVING_SPHERE: { // moving_sphere.rs:23-26,31-48
-        const float4 f = *reinterpret_cast<const float4 *>(w + 2);
-        const double s = double((r.time - f.w) * __int_as_float(tail.x));
-        return hit_sphere(l, p01.x + s * double(f.x), p01.y + s * double(f.y), p23.x + s * double(f.z), p23.y, kTMin, tmax, t);
-    }
-    case P_MEDIUM_SPHERE: { // boundary.hit(-inf, inf) then boundary.hit(t1 + 0.0001, inf), constant_medium.rs:58-72
-        if (!MEDIA) return false;
+    if (type == P_SPHERE || type == P_MOVING_SPHERE || (MEDIA && type == P_MEDIUM_SPHERE)) {
+        double cx = p01.x, cy = p01.y, cz = p23.x;
+        if (type == P_MOVING_SPHERE) { // moving_sphere.rs:23-26,31-48
+            const float4 f = *reinterpret_cast<const float4 *>(w + 2);
+            const double s = double((r.time - f.w) * __int_as_float(tail.x));
+            cx += s * double(f.x), cy += s * double(f.y), cz += s * double(f.z);
+        }
         double r0, r1;
-        if (!sphere_roots(l, p01.x, p01.y, p23.x, p23.y, r0, r1)) return false;
+        if (!sphere_roots(l, cx, cy, cz, p23.y, r0, r1)) return false;
+        if (!MEDIA || type != P_MEDIUM_SPHERE) { // sphere.rs:43-48: near root first, then far
+            double root = r0;
+            if (root < kTMin || tmax < root) {
+                root = r1;
+                if (root < kTMin || tmax < root) return false;
+            }
+            t = root;
+            return true;
+        }
+        // boundary.hit(-inf, inf) then boundary.hit(t1 + 0.0001, inf), constant_medium.rs:58-72
         if (r1 < r0 + 0.0001) return false;
         const double nid = w[2].x;
         const double len = sqrt(l.dx * l.dx + l.dy * l.dy + l.dz * l.dz);
         const uint32_t id = EXACT ? uint32_t(__ldg(sc.prim_id + leaf)) : uint32_t(leaf);
         return medium_sample<EXACT>(r0, r1, nid, len, kTMin, tmax, mr, id, t);
     }
+    switch (type) {
     case P_MEDIUM_BOX: { // the six sides of aabox.rs:29-76 as three slabs
         if (!MEDIA) return false;
         const double2 q01 = w[2];

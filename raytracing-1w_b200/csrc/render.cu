@@ -1009,15 +1009,18 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     // A/B against a split pipeline (RT1W_SPLIT_PIPELINE=1): the same wave as a shade launch + an extend launch, with the rays
     // in HBM in between.  Instantiated for the scenes the A/B is run on: medium-free flat scenes and binary-tree scenes.
     WaveKernel split_shade = nullptr, split_extend = nullptr;
-    if (args.pool.stage.a != nullptr && !persistent && !media && !wide) {
-        if (flat) {
+    if (args.pool.stage.a != nullptr && !persistent && !wide) {
+        if (flat && !media) {
             split_shade = rich ? k_wave<true, false, true, false, 1> : k_wave<true, false, false, false, 1>;
             split_extend = rich ? k_wave<true, false, true, false, 2> : k_wave<true, false, false, false, 2>;
-        } else {
+        } else if (!flat && !media) {
             split_shade = rich ? k_wave<false, false, true, false, 1> : k_wave<false, false, false, false, 1>;
             split_extend = rich ? k_wave<false, false, true, false, 2> : k_wave<false, false, false, false, 2>;
+        } else if (!flat && rich) { // final_scene
+            split_shade = k_wave<false, true, true, false, 1>;
+            split_extend = k_wave<false, true, true, false, 2>;
         }
-        if (flat) {
+        if (flat && split_shade) {
             cudaFuncSetAttribute(split_shade, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(split_extend, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
@@ -1039,6 +1042,16 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
         }
     }
     if (!perlin_in_smem) perlin_bytes = 0;
+    for (WaveKernel k : {split_shade, split_extend}) { // (A/B) the same opt-in, or no split
+        cudaFuncAttributes fa;
+        if (k == nullptr || perlin_bytes == 0) continue;
+        if (cudaFuncGetAttributes(&fa, k) != cudaSuccess ||
+            (fa.sharedSizeBytes + perlin_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(perlin_bytes)) != cudaSuccess)) {
+            cudaGetLastError();
+            split_shade = split_extend = nullptr;
+            break;
+        }
+    }
     // north_star (a): the BVH nodes "kept resident in L2".  The trees of the BASELINE scenes fit L2 many times over and are
     // hit there anyway (L2 hit rate 93 % on the 1 M-sphere scene, whose 22 MB of wide nodes compete with 64 MB of primitives
     // and the streaming queues); RT1W_L2_PERSIST=1 pins the node array with an access-policy window for the A/B.

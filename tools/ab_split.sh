@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 for mode in fused split; do
   echo "== $mode"
   for i in 1 2; do
-    env $( [ $mode = split ] && echo RT1W_SPLIT_PIPELINE=1 || echo RT1W_NOOP=1 ) timeout 600 python tools/scene_perf.py cornel_box:100 one_weekend:32 2>/dev/null | python -c "
+    env $( [ $mode = split ] && echo RT1W_SPLIT_PIPELINE=1 || echo RT1W_NOOP=1 ) timeout 600 python tools/scene_perf.py cornel_box:100 one_weekend:32 final_scene:32 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
@@ -18,7 +18,7 @@ for l in sys.stdin:
 import importlib, numpy as np
 api = importlib.import_module("raytracing-1w_b200").api
 ctx = api.Context(0)
-for name in ("cornel_box", "one_weekend"):
+for name in ("cornel_box", "one_weekend", "final_scene"):
     hs = api.HostScene(name, seed=1); sc = api.Scene(ctx, hs.desc)
     img, _, st = sc.render(hs.camera(), hs.params(width=128, spp=16, seed=3))
     np.save(f"gpurun_out/ab_split_{name}_$mode.npy", img); print(" ", name, "128 px x 16 spp:", st.rays, "rays,", st.launches, "launches")
@@ -26,7 +26,7 @@ PY
 done
 python - <<PY
 import numpy as np
-for name in ("cornel_box", "one_weekend"):
+for name in ("cornel_box", "one_weekend", "final_scene"):
     a, b = np.load(f"gpurun_out/ab_split_{name}_fused.npy"), np.load(f"gpurun_out/ab_split_{name}_split.npy")
     ok = np.isfinite(a) & np.isfinite(b)
     print(name, "same image:", bool((np.isfinite(a) == np.isfinite(b)).all() and np.allclose(a[ok], b[ok], rtol=1e-3, atol=1e-3)))

@@ -223,7 +223,7 @@ RT1W_DEV float min3(float a, float b, float c) {
 // closest root wins.
 // Sides are numbered as aabox.rs:29-76 lists them: XY@z1, XY@z0, XZ@y1, XZ@y0, YZ@x1, YZ@x0.
 // returns the first side to test | the second one << 4
-RT1W_DEV int box_first_sides(const LocalRay &l, double x0, double y0, double z0, double x1, double y1, double z1) {
+RT1W_DEV int box_first_sides(const LocalRay &l, double x0, double y0, double z0, double x1, double y1, double z1, bool &leaves_before_tmin) {
     const float ix = rcp_capped(float(l.dx)), iy = rcp_capped(float(l.dy)), iz = rcp_capped(float(l.dz));
     const float ax = float(x0 - l.ox) * ix, bx = float(x1 - l.ox) * ix;
     const float ay = float(y0 - l.oy) * iy, by = float(y1 - l.oy) * iy;
@@ -236,6 +236,11 @@ RT1W_DEV int box_first_sides(const LocalRay &l, double x0, double y0, double z0,
     const int s_in = (2 - a_in) * 2 + ((a_in == 0 ? ix : (a_in == 1 ? iy : iz)) > 0.0f ? 1 : 0);
     const int s_out = (2 - a_out) * 2 + ((a_out == 0 ? ix : (a_out == 1 ? iy : iz)) > 0.0f ? 0 : 1);
     const bool entry_first = fmaxf(fmaxf(fx, fy), fz) >= float(kTMin);
+    // The ray leaves the box well before t_min (typically: it starts ON the box, scattered off one of its sides): beyond
+    // t_min it is outside the box by at least 1e-4 |d_exit|, so no side can hold an accepted root (aabox.rs:84-103
+    // would test six rectangles and find nothing).  Only claimed when the exit axis is not grazing, so that this margin
+    // dwarfs the f64 rounding of the rectangle tests (1e-16 of the coordinates).
+    leaves_before_tmin = fminf(fminf(kx, ky), kz) < 0.0009f && fabsf(a_out == 0 ? ix : (a_out == 1 ? iy : iz)) < 1e4f;
     return entry_first ? (s_in | (s_out << 4)) : (s_out | (s_in << 4));
 }
 
@@ -280,7 +285,9 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
             const double x0 = p01.x, y0 = p01.y, z0 = p23.x, x1 = q01.x, y1 = q01.y, z1 = __hiloint2double(tail.y, tail.x);
             const bool first = box_sides == 0u;
             if (first) { // sides left to test in bits 0..5, the one to test second in bits 8..10
-                const int two = box_first_sides(l, x0, y0, z0, x1, y1, z1);
+                bool gone;
+                const int two = box_first_sides(l, x0, y0, z0, x1, y1, z1, gone);
+                if (gone) return false; // box_sides is still 0: the caller's loop over the sides ends
                 side = two & 15;
                 box_sides = 0x3fu | (uint32_t((two >> 4) | 8) << 8);
             } else if (box_sides >> 8) {
@@ -1095,7 +1102,7 @@ RT1W_DEV float perlin_turb(const DPerlin *tab, double px, double py, double pz, 
 RT1W_DEV float sin_reduced(double x) {
     const double two_pi = 6.283185307179586476925286766559;
     const double k = rint(x * (1.0 / two_pi));
-    return sinf(float(x - k * two_pi));
+    return __sinf(float(x - k * two_pi)); // the argument is in [-pi, pi]: MUFU.SIN, 2^-21 absolute (sinf: 30 instructions + a slow path that is never taken)
 }
 
 // `perlins` may point at shared memory copies of the tables (render.cu stages them per CTA).

@@ -220,3 +220,42 @@ def test_global_primitives_stay_out_of_the_tree(rt, oracle, gpu_ctx, monkeypatch
     for k in (1, 2, 3, 4):
         assert np.array_equal(a[k][same], b[k][same])
     out_of_tree.close(), in_tree.close()
+
+
+@pytest.mark.parametrize("name,extent", [("final_scene", 700.0), ("cornel_smoke", None), ("random_scene", 15.0)])
+def test_rays_starting_on_surfaces(rt, oracle, gpu_ctx, name, extent):
+    """Rays that START on a primitive - the hit points of camera rays - heading outward or inward, and rays that start
+    just INSIDE it and leave through the side they sit under at t = 1e-5 .. 1e-1 (around t_min = 0.001), with
+    un-normalised directions: what the scattered rays of a render are.  A BVH leaf that holds an AABox leaves the box
+    without testing its six sides (aabox.rs:84-103) when the f32 slab exit lies before t_min (kernels.cuh:
+    box_first_sides): here that shortcut meets exits on either side of t_min and rays that enter the box through the
+    side they start on.  Same bars as the synthetic ray set; the oracle's tie rule (a 1e-9-relative nudge of the ray
+    changes the winner) takes out the rays whose start decides by rounding which side of the surface they are on."""
+    api = rt.api
+    n = 1 << 18
+    hs = api.HostScene(name, seed=1)
+    osc = oracle.OracleScene(hs.desc)
+    gsc = api.Scene(gpu_ctx, hs.desc)
+    base = make_ray_set(api, hs, osc, gsc.prims(), n, extent)
+    prim, tt, normal, _, _, _ = osc.trace_closest(base, seed=1)
+    ok = prim >= 0
+    assert ok.mean() > 0.3
+    idx = np.flatnonzero(ok)
+    rng = np.random.Generator(np.random.Philox(0x51DE))
+    pick = idx[rng.integers(0, len(idx), n)]
+    o = base["origin"][pick].astype(np.float64) + tt[pick][:, None] * base["direction"][pick].astype(np.float64)
+    nrm = normal[pick] / np.linalg.norm(normal[pick], axis=1, keepdims=True)
+    v = rng.normal(size=(n, 3))
+    tangent = v - (v * nrm).sum(1, keepdims=True) * nrm
+    tangent /= np.linalg.norm(tangent, axis=1, keepdims=True)
+    along = 10.0 ** rng.uniform(-3.0, 0.0, (n, 1)) * np.where(rng.random((n, 1)) < 0.5, 1.0, -1.0)
+    d = (tangent * np.sqrt(np.maximum(1.0 - along * along, 0.0)) + nrm * along) * 10.0 ** rng.uniform(-1.0, 2.5, (n, 1))
+    third = n // 3  # the last third starts under the surface: it reaches it at t_exit along d
+    t_exit = 10.0 ** rng.uniform(-5.0, -1.0, (n, 1))
+    o[2 * third:] -= (t_exit * d)[2 * third:]
+    rays = np.zeros(n, dtype=api.RAY_DTYPE)
+    rays["origin"] = o
+    rays["direction"] = d
+    rays["time"] = base["time"][pick]  # a moving sphere is where the camera ray met it
+    check_trace_parity(gsc, osc, rays, label=f"{name}, rays starting on surfaces", max_ambiguous=0.3, min_hit_fraction=0.05)
+    gsc.close()

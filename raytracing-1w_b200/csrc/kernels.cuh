@@ -314,6 +314,15 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
         }
         return hit;
     }
+    if (!MEDIA) { // medium-free kernels (random_scene, one_weekend): one inlined solve per sphere kind is 1 % faster there
+        if (type == P_SPHERE) return hit_sphere(l, p01.x, p01.y, p23.x, p23.y, kTMin, tmax, t);
+        if (type == P_MOVING_SPHERE) { // moving_sphere.rs:23-26,31-48
+            const float4 f = *reinterpret_cast<const float4 *>(w + 2);
+            const double s = double((r.time - f.w) * __int_as_float(tail.x));
+            return hit_sphere(l, p01.x + s * double(f.x), p01.y + s * double(f.y), p23.x + s * double(f.z), p23.y, kTMin, tmax, t);
+        }
+        return false;
+    }
     if (type == P_SPHERE || type == P_MOVING_SPHERE || (MEDIA && type == P_MEDIUM_SPHERE)) {
         double cx = p01.x, cy = p01.y, cz = p23.x;
         if (type == P_MOVING_SPHERE) { // moving_sphere.rs:23-26,31-48

@@ -461,6 +461,8 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
             size_t found = n;
             for (size_t i = 0; i < n && found == n; ++i) {
                 if (is_global[i]) continue;
+                // (spheres and sphere-bounded media only: hit_globals carries the sphere tests alone)
+                if (!(dev[i].kind == RT1W_NODE_SPHERE || (dev[i].kind == RT1W_NODE_CONSTANT_MEDIUM && dev[i].boundary == RT1W_NODE_SPHERE))) continue;
                 bool contains = true;
                 for (int k = 0; k < 3 && contains; ++k) {
                     const double olo = lo_at[k] == i ? lo2[k] : lo1[k], ohi = hi_at[k] == i ? hi2[k] : hi1[k];

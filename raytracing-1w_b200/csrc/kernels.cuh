@@ -267,7 +267,8 @@ RT1W_DEV bool medium_sample(double t_in, double t_out, double neg_inv_density, d
 // `box_sides`: for a P_BOX the caller passes 0 on the first call and calls again while it comes back non-zero
 // (sides still to test); `side` is written with the side tested by this call.
 // BOXES = false compiles the P_BOX case out (the flat scan keeps the six rectangles, api.cu).
-template <bool EXACT, bool MEDIA, bool BOXES>
+// ROUND = true compiles everything but the sphere kinds out (hit_globals: its copy of this function is a sixth the size).
+template <bool EXACT, bool MEDIA, bool BOXES, bool ROUND = false>
 RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P, int leaf, const Ray &r, double tmax, const MediumRng &mr, double &t,
                        uint32_t &box_sides, int &side) {
     const double2 *w = reinterpret_cast<const double2 *>(P);
@@ -276,7 +277,7 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
     const int type = int(meta & 15u);
     const double2 p01 = w[0], p23 = w[1];
     const LocalRay l = to_local(tail.w < 0 ? nullptr : frame_xf(frames, tail.w), r);
-    if (type == P_XY_RECT || type == P_XZ_RECT || type == P_YZ_RECT || (BOXES && type == P_BOX)) { // one rectangle test
+    if (!ROUND && (type == P_XY_RECT || type == P_XZ_RECT || type == P_YZ_RECT || (BOXES && type == P_BOX))) { // one rectangle test
         int ax = P_YZ_RECT - type;
         double a0 = p01.x, a1 = p01.y, b0 = p23.x, b1 = p23.y, k = w[2].x;
         bool box_first = false;
@@ -350,7 +351,7 @@ RT1W_DEV bool hit_prim(const SceneView &sc, const DFrame *frames, const DPrim *P
     }
     switch (type) {
     case P_MEDIUM_BOX: { // the six sides of aabox.rs:29-76 as three slabs
-        if (!MEDIA) return false;
+        if (!MEDIA || ROUND) return false;
         const double2 q01 = w[2];
         const double q2 = __hiloint2double(tail.y, tail.x);
         const double ix = 1.0 / l.dx, iy = 1.0 / l.dy, iz = 1.0 / l.dz;
@@ -487,8 +488,9 @@ RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng 
     trav_pop(T, stack, stride, overflow);
 }
 
-// The primitives that are in no tree (api.cu: their box contains every other primitive's, e.g. a fog sphere around the
-// whole scene): tested after the traversal, against the best hit it found - the whole warp at once.
+// The primitives that are in no tree (api.cu: spheres and sphere-bounded media whose box contains every other primitive's,
+// e.g. a fog sphere around the whole scene): tested after the traversal, against the best hit it found - the whole warp
+// at once, by a sphere-only copy of hit_prim (a full second copy cost final_scene 1.4 %: instruction fetch).
 template <bool EXACT, bool MEDIA>
 RT1W_DEV void hit_globals(const SceneView &sc, const Ray &r, const MediumRng &mr, double &best, int &best_leaf) {
     for (int g = sc.n_prims - sc.n_global; g < sc.n_prims; ++g) {
@@ -497,7 +499,7 @@ RT1W_DEV void hit_globals(const SceneView &sc, const Ray &r, const MediumRng &mr
             double t;
             int side = 0;
             RT1W_TRAV_COUNT(2);
-            if (hit_prim<EXACT, MEDIA, true>(sc, sc.frames, sc.prims + g, g, r, best, mr, t, box_sides, side)) best = t, best_leaf = g | (side << kLeafBits);
+            if (hit_prim<EXACT, MEDIA, false, true>(sc, sc.frames, sc.prims + g, g, r, best, mr, t, box_sides, side)) best = t, best_leaf = g | (side << kLeafBits);
         } while (box_sides != 0u);
     }
 }
@@ -1130,7 +1132,7 @@ template <bool RICH> RT1W_DEV f3 texture_value(const SceneView &sc, const DPerli
         const float s = 0.5f * (1.0f + sin_reduced(double(t.scale) * h.pz + 10.0 * double(turb)));
         return mk3(s, s, s);
     }
-    case RT1W_TEX_PERLIN: { // perlin.rs:109-113
+    case RT1W_TEX_PERLIN: { // perlin.rs:109-113 (a second copy of the lattice code: one shared, rolled copy cost two_perlin_spheres 11 %)
         const float s = perlin_noise(perlins + t.table, h.px, h.py, h.pz);
         return mk3(s, s, s);
     }

@@ -1,2 +1,2 @@
 #!/bin/bash
-bash tools/ab_libs.sh "final_scene:32 random_scene:32:1200 one_weekend:32" librt1w variant_splitsph variant_st8 variant_st12
+bash tools/ab_libs.sh "final_scene:32 two_perlin_spheres:32:1200" librt1w variant_p2 librt1w variant_p2

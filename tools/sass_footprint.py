@@ -16,7 +16,7 @@ from ncu_regions import function_starts  # noqa: E402
 
 def main():
     want = sys.argv[1]
-    lib = os.path.join(ROOT, "raytracing-1w_b200", "_build", "librt1w.so")
+    lib = os.environ.get("RT1W_LIB") or os.path.join(ROOT, "raytracing-1w_b200", "_build", "librt1w.so")
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.run(["cuobjdump", "-xelf", "render", lib], cwd=tmp, check=True, capture_output=True)
         cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]

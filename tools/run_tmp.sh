@@ -1,2 +1,2 @@
 #!/bin/bash
-bash tools/ab_libs.sh "final_scene:32 two_perlin_spheres:32:1200" librt1w variant_p2 librt1w variant_p2
+bash tools/ab_libs.sh "cornel_box:100 cornel_smoke:32 final_scene:32" librt1w variant_opsu librt1w variant_opsu

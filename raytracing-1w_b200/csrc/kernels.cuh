@@ -135,6 +135,7 @@ RT1W_DEV LocalRay to_local(const FrameXf *f, const Ray &r) { // f == nullptr: no
 // ------------------------------------------------------------------------------------------
 // Primitive tests (f64).  Each returns the accepted root in [tmin, tmax] like the reference.
 // ------------------------------------------------------------------------------------------
+
 RT1W_DEV bool sphere_roots(const LocalRay &l, double cx, double cy, double cz, double radius, double &r0, double &r1) {
     // sphere.rs:31-41
     const double ocx = l.ox - cx, ocy = l.oy - cy, ocz = l.oz - cz;
@@ -885,13 +886,22 @@ RT1W_DEV bool closest_hit_flat(const SceneView &sc, const FlatScene &fs, const R
                 const LocalRay l = to_local(frame_xf(fs.frames, frame), r);
                 o = mk3(float(l.ox), float(l.oy), float(l.oz)), d = mk3(float(l.dx), float(l.dy), float(l.dz));
             }
-            for (; k < end; ++k, bit <<= 1) {
-                float tn;
-                const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn) && sphere_maybe(fs.sphere[k], o, d);
-                tn_col[k * stride] = tn;
-                if (in) cand |= bit;
-                if (in && tn < t1) t1 = tn, k1 = k;
+#define RT1W_SPHERE_SLOT                                                                                    \
+    {                                                                                                      \
+        float tn;                                                                                          \
+        const bool in = slab_fma(fs.lo[k], fs.hi[k], s, tn) && sphere_maybe(fs.sphere[k], o, d);           \
+        tn_col[k * stride] = tn;                                                                           \
+        if (in) cand |= bit;                                                                               \
+        if (in && tn < t1) t1 = tn, k1 = k;                                                                \
+    }
+            // measured per kernel: with the loop rolled cornel_smoke gains 2.8 % (instruction fetch), the Cornell box loses 0.6 %
+            if (MEDIA) {
+#pragma unroll 1
+                for (; k < end; ++k, bit <<= 1) RT1W_SPHERE_SLOT
+            } else {
+                for (; k < end; ++k, bit <<= 1) RT1W_SPHERE_SLOT
             }
+#undef RT1W_SPHERE_SLOT
         } else {
 #pragma unroll(kScanUnroll)
             for (; k < end; ++k, bit <<= 1) {
@@ -1110,27 +1120,31 @@ RT1W_DEV float perlin_turb(const DPerlin *tab, double px, double py, double pz, 
     return fabsf(accum);
 }
 
-// sin of a f64 argument through f32 after an f64 range reduction (arguments reach 1e4 in the scenes)
-RT1W_DEV float sin_reduced(double x) {
+// sin of a f64 argument through f32 after an f64 range reduction (arguments reach 1e4 in the scenes).
+// FAST: MUFU.SIN on the reduced argument in [-pi, pi] (2^-21 absolute) instead of sinf's 30 instructions + a slow path that
+// is never taken: random_scene +3.3 %, final_scene +2.1 % in the lockstep kernels.  The persistent kernel keeps sinf: the
+// stress scene, which never calls it, runs 4.7 % SLOWER with MUFU.SIN in the kernel (and 2 % slower with the texture code
+// compiled out altogether) - the register allocation of its traversal loop at the 128-register cap is that sensitive.
+template <bool FAST> RT1W_DEV float sin_reduced(double x) {
     const double two_pi = 6.283185307179586476925286766559;
     const double k = rint(x * (1.0 / two_pi));
-    return __sinf(float(x - k * two_pi)); // the argument is in [-pi, pi]: MUFU.SIN, 2^-21 absolute (sinf: 30 instructions + a slow path that is never taken)
+    return FAST ? __sinf(float(x - k * two_pi)) : sinf(float(x - k * two_pi));
 }
 
 // `perlins` may point at shared memory copies of the tables (render.cu stages them per CTA).
 // RICH = false: the scene has only SolidColor textures (checker, Perlin and image code compiled out).
-template <bool RICH> RT1W_DEV f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
+template <bool RICH, bool FAST_SIN = true> RT1W_DEV f3 texture_value(const SceneView &sc, const DPerlin *perlins, int tex, const HitInfo &h) {
     DTexture t = sc.textures[tex];
     if (!RICH) return mk3(t.color[0], t.color[1], t.color[2]);
     for (int guard = 0; guard < 9 && t.type == RT1W_TEX_CHECKER; ++guard) { // texture.rs:46-55
-        const float sines = sin_reduced(10.0 * h.px) * sin_reduced(10.0 * h.py) * sin_reduced(10.0 * h.pz);
+        const float sines = sin_reduced<FAST_SIN>(10.0 * h.px) * sin_reduced<FAST_SIN>(10.0 * h.py) * sin_reduced<FAST_SIN>(10.0 * h.pz);
         t = sc.textures[sines < 0.0f ? t.odd : t.even];
     }
     switch (t.type) {
     case RT1W_TEX_SOLID: return mk3(t.color[0], t.color[1], t.color[2]);
     case RT1W_TEX_NOISE: { // texture.rs:57-65
         const float turb = perlin_turb(perlins + t.table, h.px, h.py, h.pz, 7);
-        const float s = 0.5f * (1.0f + sin_reduced(double(t.scale) * h.pz + 10.0 * double(turb)));
+        const float s = 0.5f * (1.0f + sin_reduced<FAST_SIN>(double(t.scale) * h.pz + 10.0 * double(turb)));
         return mk3(s, s, s);
     }
     case RT1W_TEX_PERLIN: { // perlin.rs:109-113 (a second copy of the lattice code: one shared, rolled copy cost two_perlin_spheres 11 %)

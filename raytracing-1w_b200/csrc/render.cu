@@ -216,7 +216,7 @@ RT1W_DEV Ray generate_ray(const RenderArgs &a, uint32_t t0, uint32_t w0, uint32_
 // ------------------------------------------------------------------------------------------
 // `prims`, `frames`: the scene tables (global memory, or the flat scan's shared-memory copies).
 // MEDIA = false: no Isotropic hits can be queued (ConstantMedium::new is the only source, constant_medium.rs:22-28).
-template <bool MEDIA, bool RICH>
+template <bool MEDIA, bool RICH, bool FAST_SIN = true>
 RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, const DFrame *frames, const DPerlin *perlins, const DLight *lights,
                       Ray &r, const HitRec &hr, RayC &c, f3 &thr) {
     const DMaterial m = a.sc.materials[hr.meta >> 12];
@@ -229,7 +229,7 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
     f3 dir;
     float time = r.time; // specular scatters keep ray.time (material.rs:104,157; constant_medium.rs:46)
     if (mat == RT1W_MAT_LAMBERTIAN) {
-        const f3 att = texture_value<RICH>(a.sc, perlins, m.texture, h);
+        const f3 att = texture_value<RICH, FAST_SIN>(a.sc, perlins, m.texture, h);
         f3 weight;
         dir = scatter_lambertian(a.sc, lights, h, x0, weight);
         thr = thr * att * weight;
@@ -240,7 +240,7 @@ RT1W_DEV bool scatter(const int mat, const RenderArgs &a, const DPrim *prims, co
     } else if (mat == RT1W_MAT_DIELECTRIC || !MEDIA) {
         dir = scatter_dielectric(m, r, h, x0); // attenuation (1,1,1)
     } else {                                    // Isotropic, constant_medium.rs:36-51
-        thr = thr * texture_value<RICH>(a.sc, perlins, m.texture, h);
+        thr = thr * texture_value<RICH, FAST_SIN>(a.sc, perlins, m.texture, h);
         dir = random_in_unit_sphere(x0, rng);
     }
     if (depth + 1u >= uint32_t(a.rp.max_depth)) return false; // main.rs:59-61: the next ray_color call returns black (the caller keeps a NaN throughput alive in the pixel)
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
                         const HitRec hr = stream_load(in.h + j);
                         const float4 th4 = stream_load(in.t + j);
                         nthr = mk3(th4.x, th4.y, th4.z);
-                        alive = scatter<MEDIA, true>(scatter_mat(seg), a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr);
+                        alive = scatter<MEDIA, true, false>(scatter_mat(seg), a, a.sc.prims, a.sc.frames, perlins, s_lights, nr, hr, nc, nthr); // (sinf: see sin_reduced)
                         if (!alive && !finite3(nthr)) splat(a, nc.pixel, nthr, mk3(0.0f, 0.0f, 0.0f)); // depth limit: a NaN throughput still reaches the pixel
                     }
                 } else if (i < lay.total) { // a new camera path
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
                 }
                 if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) { // material.rs:168-181: emits on the front face only, never scatters (main.rs:110-112)
                     const HitInfo hi = finalize_hit<false>(a.sc.prims + (h.leaf & kLeafMask), a.sc.frames, h.leaf >> kLeafBits, r, h.t);
-                    const f3 e = hi.front_face ? texture_value<true>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
+                    const f3 e = hi.front_face ? texture_value<true, false>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi) : mk3(0.0f, 0.0f, 0.0f);
                     splat(a, c.pixel, thr, e);
                 } else if (mat_type == RT1W_MAT_NONE) { // main.rs:113-115 (miss -> background) or `impl Material for ()` (material.rs:68): zero radiance
                     const f3 rad = hit ? mk3(0.0f, 0.0f, 0.0f) : mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);

@@ -1,2 +1,2 @@
 #!/bin/bash
-bash tools/ab_libs.sh "cornel_box:100 cornel_smoke:32 final_scene:32" librt1w variant_opsu librt1w variant_opsu
+bash tools/ab_libs.sh "stress:8 final_scene:32 random_scene:32:1200 cornel_box:100 one_weekend:32" variant_psin librt1w

@@ -211,7 +211,7 @@ typedef struct rt1w_scene_info {
     int32_t n_wide_nodes;  /* 80-byte nodes of the compressed 8-wide BVH (0: flat-scan scene) */
     int32_t wide_depth;
     int32_t wide_default;  /* 1: render and trace calls walk the 8-wide tree unless a flag says otherwise */
-    int32_t n_global_prims; /* primitives kept out of the tree because their box contains every other one's (tested once per ray) */
+    int32_t n_global_prims; /* spheres / sphere-bounded media kept out of the tree because their box contains every other primitive's (tested once per ray) */
     double wide_children;  /* occupied slots per wide node */
 } rt1w_scene_info;
 

@@ -1,4 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-bash tools/ab_libs.sh "cornel_box:100 final_scene:32 random_scene:32:1200 one_weekend:32 stress:8" librt1w variant_fsc
-RT1W_LIB=$PWD/raytracing-1w_b200/_build/variant_fsc.so python -m pytest tests/test_gpu_shading_hooks.py -m gpu -x -q > gpurun_out/s2j_pytest.log 2>&1; echo "pytest(fsc) exit $?"; tail -2 gpurun_out/s2j_pytest.log
+for n in 2 4 8; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n > gpurun_out/s2_bench_n$n.json 2> gpurun_out/s2_bench_n$n.err || tail -5 gpurun_out/s2_bench_n$n.err
+  tail -n 1 gpurun_out/s2_bench_n$n.json | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print('N', d['n_gpus'], 'C1', round(d['value'], 1), 'ms', round(d['ms_per_step'], 3), 'e2e', round(d['e2e']['value'], 1))
+for c in d.get('configs', []): print('   ', c['name'], round(c['mpaths_per_s'], 1))
+for c in d.get('strong_scaling', []): print('   strong', c['name'], round(c['ms_per_step'], 2), 'ms', round(c['mpaths_per_s'], 1))"
+done
+python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -2

@@ -124,7 +124,28 @@ def wrapped_media_scene(api):
     return AdHoc(api, b, (278.0, 278.0, -800.0), (278.0, 278.0, 0.0), 40.0, (0.0, 0.0, 0.0))
 
 
+def enclosed_scene(api):
+    """Two primitives whose boxes contain everything else: a sky sphere (kept out of the tree and tested once per ray after
+    the traversal, kernels.cuh: hit_globals carries the sphere tests only) and, inside it, a closed AABox room around 40
+    spheres and boxes (an AABox is NOT taken out of the tree: it stays a P_BOX leaf).  The camera sits inside the room and
+    glass panes let rays out to the sky sphere."""
+    rng = np.random.Generator(np.random.Philox(17))
+    b = api.DescBuilder()
+    kids = [b.flip_face(b.sphere((0.0, 0.0, 0.0), 400.0, b.diffuse_light(b.solid(0.6, 0.7, 1.0)))),  # the sky, emitting inward (material.rs:168-181)
+            b.aabox((-100.0, -100.0, -100.0), (100.0, 100.0, 100.0), b.dielectric(1.5))]      # the room: glass all around
+    grey, gold = b.lambertian(b.solid(0.5, 0.5, 0.5)), b.metal((0.8, 0.6, 0.2), 0.1)
+    for k in range(40):
+        c = rng.uniform(-80.0, 80.0, 3)
+        if k % 4 == 0:
+            kids.append(b.aabox(tuple(c - rng.uniform(3.0, 9.0, 3)), tuple(c + rng.uniform(3.0, 9.0, 3)), gold if k % 8 else grey))
+        else:
+            kids.append(b.sphere(tuple(c), float(rng.uniform(3.0, 10.0)), grey if k % 3 else gold))
+    b.set_world(b.bvh(kids))
+    return AdHoc(api, b, (0.0, 20.0, -90.0), (0.0, 0.0, 0.0), 60.0, (0.0, 0.0, 0.0))
+
+
 SCENES = {
+    "enclosed": (enclosed_scene, {}, 1 << 16, 120.0),
     "boxes": (boxes_scene, {}, 1 << 16, None),
     "image_rects": (image_rects_scene, {}, 1 << 16, None),
     "perlin3_flat": (perlin_scene, dict(n_tables=3), 1 << 15, 12.0),
@@ -142,6 +163,8 @@ def test_adhoc_closest_hit_matches_oracle(rt, oracle, gpu_ctx, name):
     osc = oracle.OracleScene(hs.desc)
     gsc = api.Scene(gpu_ctx, hs.desc)
     info = gsc.info()
+    if name == "enclosed":  # the sky sphere is tested outside the tree, the room box inside it
+        assert info.n_global_prims == 1 and info.n_bvh_nodes > 0
     if name == "boxes":  # the six boxes travel as one primitive each: 6 + 6 leaves -> a BVH, not the scan
         assert info.n_prims == 42 and info.n_bvh_nodes >= 2 * 12 - 1
     rays = make_ray_set(api, hs, osc, gsc.prims(), n, extent)
@@ -149,7 +172,7 @@ def test_adhoc_closest_hit_matches_oracle(rt, oracle, gpu_ctx, name):
     gsc.close()
 
 
-@pytest.mark.parametrize("name,width,spp", [("boxes", 64, 256), ("image_rects", 64, 256), ("perlin3_flat", 96, 64),
+@pytest.mark.parametrize("name,width,spp", [("enclosed", 64, 128), ("boxes", 64, 256), ("image_rects", 64, 256), ("perlin3_flat", 96, 64),
                                             ("perlin8_bvh", 96, 64), ("perlin12_global", 96, 64), ("wrapped_media", 48, 256)])
 def test_adhoc_render_matches_oracle(rt, oracle, gpu_ctx, name, width, spp):
     api = rt.api

@@ -1,3 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-python -m pytest tests/test_gpu_adhoc_scenes.py -m gpu -q -k "enclosed" -rP > gpurun_out/s2k_pytest.log 2>&1; echo "pytest exit $?"; grep -a "trace parity\|passed\|failed\|Error\|assert" gpurun_out/s2k_pytest.log | head
+python tools/pool_sweep.py cornel_box 100 21 22 23 24 25 2>&1 | grep -v "^$"
+python tools/pool_sweep.py final_scene 32 22 23 24 2>&1 | grep -v "^$"
+python tools/pool_sweep.py one_weekend 32 22 23 24 25 2>&1 | grep -v "^$"

@@ -43,6 +43,15 @@ rt1w_status fail_cuda(const char *what, cudaError_t e) {
 
 constexpr uint32_t kDefaultPool = 1u << 23; // rays in flight per wave: the queues stream through HBM, so bigger waves amortise launches and the tail
 constexpr int kLbvhFromPrims = 1 << 17;      // scenes from this many primitives on get their BVH built on the device
+// The traversal's node reference (primitive count << 29 | left_first) folded into the first word of every node once, so that
+// a node step reads it instead of combining two words per child (kernels.cuh: node_ref)
+__global__ void k_fold_node_refs(uint4 *nodes, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) nodes[2 * i].w |= nodes[2 * i + 1].w << 29;
+}
+static void fold_node_refs(float4 *nodes, size_t n, cudaStream_t stream) {
+    k_fold_node_refs<<<unsigned((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<uint4 *>(nodes), n);
+}
 constexpr int kWideFromNodes = 32768;        // BVHs from this many binary nodes on are walked through the compressed 8-wide tree by default
 constexpr int kMaxLeaf = 1; // single-primitive leaves: the f32 leaf-box test screens the f64 primitive solve
 
@@ -630,6 +639,7 @@ static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *d
         RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_nodes), sizeof(BvhNode32) * bvh.nodes.size()));
         RT1W_CUDA(cudaMemcpy(s->d_nodes, bvh.nodes.data(), sizeof(BvhNode32) * bvh.nodes.size(), cudaMemcpyHostToDevice));
     }
+    if (n_bvh_nodes > 0) fold_node_refs(s->d_nodes, n_bvh_nodes, ctx->stream);
     if (!wide.nodes.empty() && wide.depth <= kWideMaxDepth) {
         static_assert(sizeof(Bvh8Node) == 5 * sizeof(uint4), "wide node layout");
         RT1W_CUDA(cudaMalloc(reinterpret_cast<void **>(&s->d_wide_nodes), sizeof(Bvh8Node) * wide.nodes.size()));

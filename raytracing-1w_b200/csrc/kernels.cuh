@@ -387,13 +387,17 @@ RT1W_DEV bool slab(const float4 lo, const float4 hi, const SlabRay &s, float tma
     const float az = fmaf(lo.z, s.iz, s.oz), bz = fmaf(hi.z, s.iz, s.oz);
     const float tn = fmaxf(max3(fminf(ax, bx), fminf(ay, by), fminf(az, bz)), 0.0f);
     float tf = fminf(min3(fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)), tmax);
-    tf = tf * 1.0000005f; // keep the f32 test conservative w.r.t. the f64 primitive solve
+    // (no slack on the comparison: the node boxes are padded by 1e-6 of the scene's reach, bvh.h: traversal_pad, eight times
+    // the 2^-23 relative rounding of the FMA form for any hit within the scene's reach of the origin, and the best hit's
+    // f32 bound is rounded up)
     tnear = tn;
     return tn <= tf;
 }
 
 // Node references on the traversal stack: primitive count in the top 3 bits, left_first below.
-RT1W_DEV uint32_t node_ref(float4 n0, float4 n1) { return (__float_as_uint(n1.w) << 29) | __float_as_uint(n0.w); }
+// (the count sits in the top 3 bits of a node's first word: api.cu folds it in after the upload, k_fold_node_refs - one word
+// read per child instead of two combined; binary steps are 62 instructions, every one of them counts)
+RT1W_DEV uint32_t node_ref(float4 n0, float4) { return __float_as_uint(n0.w); }
 
 // Traversal state of one ray, resumable step by step (the wave kernel interleaves the steps of a warp's rays
 // with refills of its idle lanes; the parity kernel just runs them to the end).
@@ -408,6 +412,7 @@ struct Trav {
     int best_leaf;  // leaf | side << kLeafBits, or -1
     uint32_t ref;   // node to visit next: interior (count bits 0), leaf, or kTravDone
     int sp;
+    uint32_t sbase; // shared-window address of the thread's stack column, held in a register (trav_bind_stack)
 };
 
 #ifdef RT1W_COUNT_TRAV // measurement build (build.py --variant trav -DRT1W_COUNT_TRAV): rays, interior steps, primitive tests, warp-level interior steps
@@ -417,6 +422,18 @@ static __device__ unsigned long long g_trav_counts[4];
 #define RT1W_TRAV_COUNT(k)
 #endif
 
+// The stack column's shared-memory address as an opaque 32-bit value: left to itself the compiler re-derives it on EVERY node
+// step (S2UR SR_CgaCtaId, UMOV, ULEA, S2R SR_TID, LEA: 5 of a step's 52 instructions) rather than keep one register alive.
+RT1W_DEV void trav_bind_stack(Trav &T, const uint2 *stack) {
+    T.sbase = uint32_t(__cvta_generic_to_shared(stack));
+    asm volatile("" : "+r"(T.sbase));
+}
+RT1W_DEV void stack_store(uint32_t addr, uint2 e) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(e.x), "r"(e.y) : "memory"); }
+RT1W_DEV uint2 stack_load(uint32_t addr) {
+    uint2 e;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr) : "memory");
+    return e;
+}
 RT1W_DEV void trav_begin(const SceneView &sc, const Ray &r, Trav &T) {
     RT1W_TRAV_COUNT(0);
     T.s.ix = rcp_capped(r.dx), T.s.iy = rcp_capped(r.dy), T.s.iz = rcp_capped(r.dz);
@@ -436,7 +453,7 @@ RT1W_DEV void trav_pop(Trav &T, const uint2 *stack, int stride, const uint2 *ove
     // (taking one entry per step instead of looping here was measured slower: 479 vs 507 Mrays/s on the 1 M-sphere scene)
     while (T.sp > 0) {
         --T.sp;
-        const uint2 e = T.sp < kStackSmem ? stack[T.sp * stride] : overflow[T.sp - kStackSmem];
+        const uint2 e = T.sp < kStackSmem ? stack_load(T.sbase + uint32_t(T.sp * stride) * 8u) : overflow[T.sp - kStackSmem];
         if (__uint_as_float(e.y) <= T.bestf) {
             T.ref = e.x;
             return;
@@ -451,7 +468,7 @@ RT1W_DEV void trav_step_interior(const SceneView &sc, Trav &T, uint2 *stack, int
 #ifdef RT1W_COUNT_TRAV
     if (int(threadIdx.x & 31) == __ffs(int(__activemask())) - 1) RT1W_TRAV_COUNT(3);
 #endif
-    const float4 *c = sc.nodes + 2 * T.ref;
+    const float4 *c = sc.nodes + 2 * size_t(T.ref); // (one IMAD.WIDE: ref * 32 bytes)
     const float4 l0 = __ldg(c), l1 = __ldg(c + 1), r0 = __ldg(c + 2), r1 = __ldg(c + 3);
     float tl, tr;
     const bool hl = slab(l0, l1, T.s, T.bestf, tl), hr = slab(r0, r1, T.s, T.bestf, tr);
@@ -459,7 +476,7 @@ RT1W_DEV void trav_step_interior(const SceneView &sc, Trav &T, uint2 *stack, int
     if (hl && hr) {
         const bool left_near = tl <= tr;
         const uint2 far_e = make_uint2(left_near ? refr : refl, __float_as_uint(left_near ? tr : tl));
-        if (T.sp < kStackSmem) stack[T.sp * stride] = far_e;
+        if (T.sp < kStackSmem) stack_store(T.sbase + uint32_t(T.sp * stride) * 8u, far_e);
         else overflow[T.sp - kStackSmem] = far_e;
         ++T.sp;
         T.ref = left_near ? refl : refr;
@@ -511,6 +528,7 @@ template <bool EXACT, bool MEDIA>
 RT1W_DEV bool closest_hit(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
     uint2 overflow[kStackLocal];
     Trav T;
+    trav_bind_stack(T, stack);
     trav_begin(sc, r, T);
     while (!trav_done(T)) {
         while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, overflow);
@@ -561,6 +579,7 @@ RT1W_DEV uint32_t octant_order(uint32_t m, uint32_t oct) {
 // the pending slot (bits 8..15 of y) a ray of octant `oct` visits next: the one with the highest slot ^ oct
 RT1W_DEV uint32_t next_slot(uint32_t y, uint32_t oct) { return (31u - uint32_t(__clz(int(octant_order(y >> 8, oct))))) ^ oct; }
 
+RT1W_DEV void trav_bind_stack(TravW &, const uint2 *) {} // (measured on the wide tree too: nothing, 190 of a step's 230 instructions are the box tests)
 RT1W_DEV void trav_reset(TravW &T) { T.ng = make_uint2(0u, 0u), T.lg = make_uint2(0u, 0u), T.sp = 0; }
 RT1W_DEV bool trav_at_leaf(const TravW &T) { return (T.lg.y >> 8) != 0u; }
 RT1W_DEV bool trav_interior(const TravW &T) { return (T.lg.y >> 8) == 0u && ((T.ng.y >> 8) != 0u || T.sp > 0); }
@@ -664,6 +683,7 @@ RT1W_DEV void trav_step_leaf(const SceneView &sc, const Ray &r, const MediumRng 
 template <bool EXACT, bool MEDIA>
 RT1W_DEV bool closest_hit_wide(const SceneView &sc, const Ray &r, const MediumRng &mr, uint2 *stack, int stride, double &t_best, int &leaf_best) {
     TravW T;
+    trav_bind_stack(T, stack);
     trav_begin(sc, r, T);
     for (;;) {
         while (trav_interior(T)) trav_step_interior(sc, T, stack, stride, nullptr);

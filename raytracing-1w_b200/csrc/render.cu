@@ -667,6 +667,7 @@ __global__ void __launch_bounds__(kWaveThreads, RT1W_PERSISTENT_MIN_BLOCKS)
     f3 thr;
     typename TravOf<WIDE>::type T;
     trav_reset(T);
+    trav_bind_stack(T, stack);
     for (;;) {
         // ---- produce: one 32-item block -> scatter / generate with the whole warp -> surviving rays into the ring
         if (more && ring_cnt <= uint32_t(kRing - 32)) {

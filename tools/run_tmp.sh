@@ -1,4 +1,4 @@
 #!/bin/bash
-python tools/pool_sweep.py cornel_box 100 21 22 23 24 25 2>&1 | grep -v "^$"
-python tools/pool_sweep.py final_scene 32 22 23 24 2>&1 | grep -v "^$"
-python tools/pool_sweep.py one_weekend 32 22 23 24 25 2>&1 | grep -v "^$"
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/s2n_pytest.log 2>&1; echo "pytest exit $?"; tail -2 gpurun_out/s2n_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

@@ -61,9 +61,12 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
     out = {}
-    committed = os.path.join(ROOT, "profiles", f"{tag}_flops.json")
-    if os.path.exists(committed):  # a partial re-capture (profiles_capture.sh TAG "C2") keeps the other configs' records
-        out = json.load(open(committed))
+    # a partial re-capture (profiles_capture.sh TAG "C2") keeps the other configs' records: those of an earlier partial digest
+    # into the same directory, else the committed ones
+    for earlier in (os.path.join(out_dir, f"{tag}_flops.json"), os.path.join(ROOT, "profiles", f"{tag}_flops.json")):
+        if os.path.exists(earlier):
+            out = json.load(open(earlier))
+            break
     for c in CONFIGS:
         base = os.path.join(ROOT, "gpurun_out", f"{tag}_{c}")
         if not os.path.exists(base + "_flops.csv"):

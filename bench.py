@@ -53,13 +53,13 @@ METRIC = "Mpaths/s (Cornell box 600x600, 100 spp per GPU, depth 50)"
 # section 3's 16 / 8 / 4 spp, 8 - 25 s of work for the host cores each.
 CONFIGS = [
     dict(name="C2", scene="random_scene", workload="random_scene (main.rs:192-295,816-827: ~485 spheres, 1 in 5 moving, aperture 0.1) 1200x800, depth 50",
-         width=1200, height=800, spp=32, full_spp=500, cpu=(1200, 800, 16)),
+         width=1200, height=800, spp=128, full_spp=500, cpu=(1200, 800, 16)),
     dict(name="C2w", scene="one_weekend", workload="One-Weekend flavour of config 2 (static spheres, fuzz U[0,0.5)) 1200x800, depth 50",
-         width=1200, height=800, spp=32, full_spp=500, cpu=(1200, 800, 16)),
+         width=1200, height=800, spp=128, full_spp=500, cpu=(1200, 800, 16)),
     dict(name="C3", scene="final_scene", workload="final_scene (main.rs:635-795,916-936: 400 boxes, media, Perlin, earth map, 1000-sphere cluster) 800x800, depth 50",
-         width=800, height=800, spp=32, full_spp=10000, cpu=(800, 800, 8)),
+         width=800, height=800, spp=128, full_spp=10000, cpu=(800, 800, 8)),
     dict(name="C5", scene="stress", workload="stress scene (SURVEY.md 8d: 10^6 random spheres + 16 rectangle lights, device-built BVH) 1920x1080, depth 50",
-         width=1920, height=1080, spp=8, full_spp=256, cpu=(1920, 1080, 4)),
+         width=1920, height=1080, spp=64, full_spp=256, cpu=(1920, 1080, 4)),
 ]
 # Strong scaling: a FIXED job split over the ranks by the library's shard rule (total spp)
 STRONG = [

@@ -451,7 +451,9 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
 // ends: no barrier between bounces, the warp diverges over materials and depths instead.  Same scatter, same closest hit,
 // same Philox counters as the waves: the image does not depend on when (or whether) it takes over.
 // The last CTA to finish zeroes the queue counters it consumed, so the waves launched after it find nothing to do.
-template <bool FLAT, bool MEDIA, bool RICH>
+// WIDE / FAST_SIN: the scenes of the persistent kernel (k_wave_bvh below) end the same way, on the tree and with the sine
+// that kernel uses, so that the image does not depend on when the tail takes over.
+template <bool FLAT, bool MEDIA, bool RICH, bool WIDE = false, bool FAST_SIN = true>
 __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLAT, MEDIA))
     k_tail(const __grid_constant__ RenderArgs a, const int slot, const int parity, const int perlin_in_smem, const uint32_t max_items) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
         f3 thr = mk3(th4.x, th4.y, th4.z);
         int mat = scatter_mat(seg);
         for (;;) { // one bounce per trip: scatter at the hit, closest hit of the scattered ray
-            if (!scatter<MEDIA, RICH>(mat, a, prims, frames, perlins, s_lights, r, hr, c, thr)) { // depth limit: zero radiance
+            if (!scatter<MEDIA, RICH, FAST_SIN>(mat, a, prims, frames, perlins, s_lights, r, hr, c, thr)) { // depth limit: zero radiance
                 if (!finite3(thr)) splat(a, c.pixel, thr, mk3(0.0f, 0.0f, 0.0f));
                 break;
             }
@@ -511,8 +513,9 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
                 mr.c0 = uint32_t(a.rp.sample_begin) + (c.state >> 8), mr.c1 = c.state & 255u, mr.c2 = purpose_word(a.rp, RNG_MEDIUM);
             }
             HitRec h;
-            const bool hit = FLAT ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kThreads, hr.leaf, h.t, h.leaf)
-                                  : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
+            const bool hit = FLAT   ? closest_hit_flat<false, MEDIA>(a.sc, s_flat[0], r, mr, s_tn + threadIdx.x, kThreads, hr.leaf, h.t, h.leaf)
+                             : WIDE ? closest_hit_wide<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf)
+                                    : closest_hit<false, MEDIA>(a.sc, r, mr, s_stack + threadIdx.x, kWaveThreads, h.t, h.leaf);
             int mat_type = RT1W_MAT_NONE;
             if (hit) {
                 h.meta = FLAT ? s_flat[0].prims[h.leaf & kLeafMask].meta : __ldg(&a.sc.prims[h.leaf & kLeafMask].meta);
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(wave_threads(FLAT, MEDIA), wave_min_blocks(FLA
                 f3 rad = mk3(0.0f, 0.0f, 0.0f);
                 if (mat_type == RT1W_MAT_DIFFUSE_LIGHT) {
                     const HitInfo hi = finalize_hit<false>(prims + (h.leaf & kLeafMask), frames, h.leaf >> kLeafBits, r, h.t);
-                    if (hi.front_face) rad = texture_value<RICH>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
+                    if (hi.front_face) rad = texture_value<RICH, FAST_SIN>(a.sc, perlins, a.sc.materials[h.meta >> 12].texture, hi);
                 } else if (!hit) {
                     rad = mk3(a.rp.background[0], a.rp.background[1], a.rp.background[2]);
                 }
@@ -1079,7 +1082,10 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     // the kernel that runs the last paths to completion (k_tail); RT1W_FLAG_NO_TAIL keeps waves to the end (A/B, tests)
     using TailKernel = void (*)(const RenderArgs, const int, const int, const int, const uint32_t);
     TailKernel tail_kernel = nullptr;
-    if (!persistent && !wide && !(args.rp.flags & RT1W_FLAG_NO_TAIL))
+    if (!flat && persistent && !(args.rp.flags & RT1W_FLAG_NO_TAIL)) // the persistent kernel's build of the shading code: every texture kind, sinf
+        tail_kernel = wide ? (media ? k_tail<false, true, true, true, false> : k_tail<false, false, true, true, false>)
+                           : (media ? k_tail<false, true, true, false, false> : k_tail<false, false, true, false, false>);
+    else if (!wide && !(args.rp.flags & RT1W_FLAG_NO_TAIL))
         tail_kernel = flat ? (media ? (rich ? k_tail<true, true, true> : k_tail<true, true, false>) : (rich ? k_tail<true, false, true> : k_tail<true, false, false>))
                            : (media ? (rich ? k_tail<false, true, true> : k_tail<false, true, false>) : (rich ? k_tail<false, false, true> : k_tail<false, false, false>));
     if (tail_kernel && flat) cudaFuncSetAttribute(tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1087,7 +1093,9 @@ cudaError_t render_waves(const RenderArgs &args, int material_mask, Counters *h_
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, perlin_bytes)) != cudaSuccess) return e;
     const int blocks = sm_count * (per_sm > 0 ? per_sm : 1);
-    const uint32_t tail_items = uint32_t(blocks) * uint32_t(threads); // one queued hit per resident thread
+    uint32_t tail_items = uint32_t(blocks) * uint32_t(threads); // one queued hit per resident thread
+    if (const char *env = std::getenv("RT1W_TAIL_FACTOR")) // (A/B: take over earlier / later; a thread then follows several paths, one after the other)
+        tail_items = uint32_t(std::min(double(args.pool.capacity), std::max(1.0, std::atof(env) * double(tail_items))));
     if (tail_kernel && perlin_bytes > 0) { // the same shared-memory opt-in as the wave kernel's (or no tail kernel)
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, tail_kernel) != cudaSuccess ||

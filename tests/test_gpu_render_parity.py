@@ -131,3 +131,23 @@ def test_tail_kernel_changes_nothing(rt, gpu_ctx, name, width, spp):
     c = gsc.render(cam, hs.params(width=width, spp=spp, seed=7, pool_paths=4096))  # many small waves, the tail kernel right away
     check_same_render(a, c, name + ", small pool")
     gsc.close()
+
+
+@pytest.mark.parametrize("name,kw,width,spp,layout", [("random_scene", {}, 128, 8, "binary"), ("final_scene", {}, 64, 8, "wide"),
+                                                      ("stress", dict(stress_spheres=100_000), 160, 8, None)])
+def test_tail_kernel_of_the_persistent_scenes(rt, gpu_ctx, name, kw, width, spp, layout):
+    """Scenes of the persistent wave kernel (k_wave_bvh: big trees, or forced) end the same way: k_tail on the tree and with the
+    sine that kernel uses (render.cu: k_tail<.., WIDE, FAST_SIN = false>) - the same image as waves to the end."""
+    api = rt.api
+    hs = api.HostScene(name, seed=1, **kw)
+    gsc = api.Scene(gpu_ctx, hs.desc)
+    cam = hs.camera()
+    flags = api.FLAG_BVH_PERSISTENT | {"binary": api.FLAG_BVH_BINARY, "wide": api.FLAG_BVH_WIDE, None: 0}[layout]
+    a = gsc.render(cam, hs.params(width=width, spp=spp, seed=7, flags=flags))
+    b = gsc.render(cam, hs.params(width=width, spp=spp, seed=7, flags=flags | api.FLAG_NO_TAIL))
+    check_same_render(a, b, f"{name}, persistent kernel, {layout or 'default'} tree")
+    assert a[2].waves < b[2].waves  # the tail kernel took over before depth 50
+    c = gsc.render(cam, hs.params(width=width, spp=spp, seed=7, flags=flags, pool_paths=4096))
+    check_same_render(a, c, name + ", persistent kernel, small pool")
+    gsc.close()
+

@@ -264,6 +264,10 @@ void rt1w_context_destroy(rt1w_context *ctx);
  * ranks' output pointers may be NULL; after rt1w_render_device their buffers hold their own partial sums).
  * rt1w_render_stats then counts this rank's paths and rays (multi-process) or all devices' (multi-device context), and
  * render_ms includes the reduce.
+ * Errors: a multi-device context checks the arguments and allocates every device's queues BEFORE any device starts, so a
+ * call either fails on all devices or reaches the reduce on all of them.  Across processes (b) the usual rule of
+ * collectives holds: a rank that returns an error before the reduce (bad arguments are rejected identically everywhere;
+ * an allocation failure is not) leaves the other ranks waiting - destroy the contexts of a failed job.
  *
  *  (a) one process, n devices - what the reference's single `main` would use:
  *        rt1w_context_create_multi(ids, n, &ctx);  rt1w_scene_create(ctx, ...);  rt1w_render(scene, ...);

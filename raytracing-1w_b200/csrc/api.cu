@@ -779,10 +779,12 @@ static rt1w_status ensure_buffers(rt1w_context *ctx, size_t pixels, bool stat, b
 // One device's part of a render call: its share of the sample range (all of it outside a communicator), then - inside a
 // communicator - the one exchange step of the path, ncclReduce(sum, fp32) of the radiance sums to rank 0 on the render
 // stream.  d_accum / d_stat: this device's buffers; after the call rank 0's hold the whole image.
-static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *d_accum, float *d_stat,
-                                 cudaStream_t stream, rt1w_render_stats *stats) {
+// Everything of a render call that can fail before the first launch: argument checks, this rank's share of the sample range,
+// the wave capacity and the queue allocation.  render_dispatch runs it for EVERY device of a multi-device context before any
+// of them starts: a device that failed here alone would leave the others waiting in the reduce.
+static rt1w_status render_prepare(rt1w_scene *scene, const rt1w_render_params *params, rt1w_render_params &p, uint32_t &want_pool, int32_t &my_samples) {
     rt1w_context *ctx = scene->ctx;
-    rt1w_render_params p = *params;
+    p = *params;
     if (p.width <= 0 || p.height <= 0) return fail(RT1W_ERR_INVALID, "image size must be positive");
     if (p.sample_end <= p.sample_begin || p.sample_begin < 0) return fail(RT1W_ERR_INVALID, "empty sample range");
     if (p.sample_end - p.sample_begin >= (1 << 24)) return fail(RT1W_ERR_UNSUPPORTED, "more than 2^24-1 samples per pixel in one call");
@@ -791,9 +793,9 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
     if (p.pool_paths > (1 << 30)) return fail(RT1W_ERR_UNSUPPORTED, "pool_paths must not exceed 2^30");
     const bool sharded = ctx->comm != nullptr && ctx->comm_size > 1;
     if (sharded) rt1w_shard_sample_range(ctx->comm_rank, ctx->comm_size, params->sample_begin, params->sample_end, &p.sample_begin, &p.sample_end);
-    const int32_t my_samples = p.sample_end - p.sample_begin; // 0: more ranks than samples - this one only joins the reduce
+    my_samples = p.sample_end - p.sample_begin; // 0: more ranks than samples - this one only joins the reduce
     const uint64_t all_paths = uint64_t(p.width) * uint64_t(p.height) * uint64_t(my_samples);
-    uint32_t want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
+    want_pool = p.pool_paths > 0 ? uint32_t(p.pool_paths) : kDefaultPool;
     if (p.pool_paths <= 0 && all_paths < want_pool) want_pool = uint32_t((all_paths + 1023u) & ~uint64_t(1023u)); // small renders: one wave holds every path
     if (want_pool == 0) want_pool = 1024;
     if (ctx->pool.allocated < want_pool || (ctx->pool.material_mask & scene->material_mask) != scene->material_mask) {
@@ -801,6 +803,18 @@ static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, c
         cudaError_t e = pool_alloc(ctx->pool, grow, scene->material_mask | ctx->pool.material_mask);
         if (e != cudaSuccess) return fail_cuda("path pool allocation", e);
     }
+    return RT1W_OK;
+}
+
+static rt1w_status render_common(rt1w_scene *scene, const rt1w_camera *camera, const rt1w_render_params *params, float *d_accum, float *d_stat,
+                                 cudaStream_t stream, rt1w_render_stats *stats) {
+    rt1w_context *ctx = scene->ctx;
+    rt1w_render_params p;
+    uint32_t want_pool = 0;
+    int32_t my_samples = 0;
+    const rt1w_status prepared = render_prepare(scene, params, p, want_pool, my_samples);
+    if (prepared != RT1W_OK) return prepared;
+    const bool sharded = ctx->comm != nullptr && ctx->comm_size > 1;
     RenderArgs args;
     args.sc = scene->view;
     args.pool = ctx->pool;
@@ -873,6 +887,21 @@ static rt1w_status render_dispatch(rt1w_scene *scene, const rt1w_camera *camera,
     std::vector<rt1w_status> status(n, RT1W_OK);
     std::vector<std::string> message(n);
     std::vector<rt1w_render_stats> st(n);
+    // whatever can fail before the first launch fails HERE, for every device, before any of them enters the collective part
+    for (size_t i = 0; i < n; ++i) {
+        rt1w_context *c = i == 0 ? ctx : ctx->members[i - 1];
+        rt1w_render_params p;
+        uint32_t want_pool = 0;
+        int32_t my_samples = 0;
+        rt1w_status s0 = cudaSetDevice(c->device) == cudaSuccess ? RT1W_OK : fail(RT1W_ERR_CUDA, "cudaSetDevice failed");
+        if (s0 == RT1W_OK && i > 0) s0 = ensure_buffers(c, pixels, d_stat != nullptr, false);
+        if (s0 == RT1W_OK) s0 = render_prepare(i == 0 ? scene : scene->replicas[i - 1], params, p, want_pool, my_samples);
+        if (s0 != RT1W_OK) {
+            const std::string why = g_error;
+            cudaSetDevice(ctx->device);
+            return fail(s0, "device " + std::to_string(i) + ": " + why);
+        }
+    }
     auto run = [&](size_t i) {
         rt1w_context *c = i == 0 ? ctx : ctx->members[i - 1];
         rt1w_scene *sc = i == 0 ? scene : scene->replicas[i - 1];
@@ -882,11 +911,8 @@ static rt1w_status render_dispatch(rt1w_scene *scene, const rt1w_camera *camera,
         }
         float *acc = d_accum, *stt = d_stat;
         cudaStream_t str = stream;
-        if (i > 0) {
-            status[i] = ensure_buffers(c, pixels, d_stat != nullptr, false);
-            acc = c->d_accum, stt = d_stat ? c->d_stat : nullptr, str = c->stream;
-        }
-        if (status[i] == RT1W_OK) status[i] = render_common(sc, camera, params, acc, stt, str, &st[i]);
+        if (i > 0) acc = c->d_accum, stt = d_stat ? c->d_stat : nullptr, str = c->stream;
+        status[i] = render_common(sc, camera, params, acc, stt, str, &st[i]);
         if (status[i] != RT1W_OK) message[i] = g_error;
     };
     std::vector<std::thread> workers;

@@ -224,10 +224,11 @@ def test_scatter_on_device(cornell, oracle):
     assert rect.sum() > 1000 and np.abs(dirs[rect] - want[rect]).max() <= 1e-3          # aarect.rs:140-147, un-normalised
     sph = to_light & (pick == 1)
     axis = np.where(sph[:, None], np.array([GLASS[0]]) - p, on)
-    cos_max = np.sqrt(np.maximum(1 - GLASS[1] ** 2 / (axis * axis).sum(1), 0.0))
-    z = np.where(sph, 1 + r2 * (cos_max - 1), np.sqrt(1 - r2))                              # math.rs:39-65
-    q = np.sqrt(np.maximum(1 - z * z, 0.0))
-    local = _onb_local(axis, np.cos(2 * np.pi * r1) * q, np.sin(2 * np.pi * r1) * q, z)
+    with np.errstate(divide="ignore", invalid="ignore"):  # rows of rays that missed (axis = 0) are masked out below
+        cos_max = np.sqrt(np.maximum(1 - GLASS[1] ** 2 / (axis * axis).sum(1), 0.0))
+        z = np.where(sph, 1 + r2 * (cos_max - 1), np.sqrt(1 - r2))                          # math.rs:39-65
+        q = np.sqrt(np.maximum(1 - z * z, 0.0))
+        local = _onb_local(axis, np.cos(2 * np.pi * r1) * q, np.sin(2 * np.pi * r1) * q, z)
     onb = lam & ~rect
     assert sph.sum() > 1000 and np.abs(dirs[onb] - local[onb]).max() <= 2e-4
     nrm = on / np.maximum(np.linalg.norm(on, axis=1, keepdims=True), 1e-30)

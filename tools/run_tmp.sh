@@ -1,4 +1,5 @@
 #!/bin/bash
+# scratch command file for short gpurun calls (edit, then: gpurun --timeout 300 -- 'bash tools/run_tmp.sh')
 mkdir -p gpurun_out
-T0=$SECONDS
-timeout 400 python -m pytest tests -m gpu -x -q -rs > gpurun_out/s3c_pytest.log 2>&1; echo "pytest exit $? after $((SECONDS - T0)) s"; tail -8 gpurun_out/s3c_pytest.log
+python -m pytest tests -m gpu -x -q -rs > gpurun_out/tmp_pytest.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/tmp_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

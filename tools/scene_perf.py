@@ -8,6 +8,8 @@ import os
 import sys
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
@@ -44,7 +46,10 @@ def main():
             "upload_ms": round(info.upload_ms, 1), "render_ms": round(st.render_ms, 2), "mpaths_s": round(st.paths / st.render_ms / 1e3, 1),
             "mrays_s": round(st.rays / st.render_ms / 1e3, 1), "rays_per_path": round(st.rays / st.paths, 3), "waves": st.waves,
             "kernel_ms": {api.KERNEL_NAMES[k]: round(sp.kernel_ms[k], 2) for k in range(7) if sp.kernel_launches[k]},
-            "nan_pixels": int((img != img).any(axis=2).sum())}), flush=True)
+            "nan_pixels": int((img != img).any(axis=2).sum()),
+            # A/B of code that must not change results: the ray count is exact (every path decision is deterministic), the image sum
+            # equal up to the order of the fp32 atomic additions
+            "rays": int(st.rays), "image_sum": float(np.nansum(img.astype(np.float64)))}), flush=True)
         scene.close()
     ctx.close()
 

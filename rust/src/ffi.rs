@@ -131,6 +131,47 @@ pub struct rt1w_render_stats {
     pub kernel_ms: [f64; 7],
     pub kernel_launches: [u64; 7],
 }
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct rt1w_scene_info {
+    pub n_prims: i32,
+    pub n_bvh_nodes: i32,
+    pub n_frames: i32,
+    pub n_lights: i32,
+    pub bvh_depth: i32,
+    pub material_mask: i32,
+    pub build_ms: f64,
+    pub upload_ms: f64,
+    pub sah_cost: f64,
+    pub n_wide_nodes: i32,
+    pub wide_depth: i32,
+    pub wide_default: i32,
+    pub n_global_prims: i32,
+    pub wide_children: f64,
+}
+/// One lowered primitive in primitive-id order (the ids `rt1w_trace_closest` reports).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rt1w_flat_prim {
+    pub kind: i32,
+    pub node: i32,
+    pub material: i32,
+    pub frame: i32,
+    pub flags: i32,
+    pub boundary: i32,
+    pub p: [f64; 10],
+    pub bbox_min: [f64; 3],
+    pub bbox_max: [f64; 3],
+    pub time0: f64,
+    pub time1: f64,
+}
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct rt1w_ray {
+    pub origin: [f32; 3],
+    pub direction: [f32; 3],
+    pub time: f32,
+}
 pub const RT1W_COMM_ID_BYTES: usize = 128;
 pub enum rt1w_context {}
 pub enum rt1w_scene {}
@@ -174,6 +215,56 @@ extern "C" {
         stats: *mut rt1w_render_stats,
     ) -> i32;
     pub fn rt1w_resolve_rgb8(rgb_sum: *const f32, width: i32, height: i32, samples_per_pixel: i32, out_rgb8: *mut u8);
+
+    // ---- scene introspection and the parity hooks (include/rt1w.h: test-only entry points) - what a `#[cfg(test)]` module of
+    // the reference would hold `Hittable::hit`, `pdf_value`, `Texture::value`, `Perlin::noise/turb`, `refract` / `reflectance`
+    // and `Material::scatter` against, value by value.  All buffers are host buffers.
+    pub fn rt1w_scene_get_info(scene: *const rt1w_scene, out: *mut rt1w_scene_info) -> i32;
+    pub fn rt1w_scene_get_prims(scene: *const rt1w_scene, out: *mut rt1w_flat_prim, capacity: i32, n_out: *mut i32) -> i32;
+    pub fn rt1w_lower_prims(desc: *const rt1w_scene_desc, out: *mut rt1w_flat_prim, capacity: i32, n_out: *mut i32) -> i32;
+    pub fn rt1w_lower_face_groups(
+        desc: *const rt1w_scene_desc,
+        group_of_prim: *mut i32,
+        face_of_prim: *mut i32,
+        capacity: i32,
+        n_groups: *mut i32,
+    ) -> i32;
+    pub fn rt1w_trace_closest(
+        scene: *mut rt1w_scene,
+        rays: *const rt1w_ray,
+        n: usize,
+        seed: u64,
+        prim_id: *mut i32,
+        t: *mut f32,
+        normal3: *mut f32,
+        front_face: *mut u8,
+        uv2: *mut f32,
+    ) -> i32;
+    pub fn rt1w_eval_light_pdf(scene: *mut rt1w_scene, light: i32, origin3: *const f64, dir3: *const f32, n: usize, pdf: *mut f32) -> i32;
+    pub fn rt1w_eval_texture(scene: *mut rt1w_scene, texture: i32, p3: *const f64, uv2: *const f32, n: usize, rgb3: *mut f32) -> i32;
+    pub fn rt1w_eval_perlin(scene: *mut rt1w_scene, table: i32, turb_depth: i32, p3: *const f64, n: usize, out: *mut f32) -> i32;
+    pub fn rt1w_eval_dielectric(
+        ctx: *mut rt1w_context,
+        unit_dir3: *const f32,
+        normal3: *const f32,
+        ratio: *const f32,
+        n: usize,
+        reflect3: *mut f32,
+        refract3: *mut f32,
+        reflectance: *mut f32,
+    ) -> i32;
+    pub fn rt1w_eval_scatter(
+        scene: *mut rt1w_scene,
+        rays: *const rt1w_ray,
+        n: usize,
+        seed: u64,
+        prim_id: *mut i32,
+        material_type: *mut i32,
+        dir3: *mut f32,
+        weight3: *mut f32,
+        time: *mut f32,
+    ) -> i32;
+    pub fn rt1w_philox4x32(counter: *const u32, key: *const u32, out: *mut u32);
 }
 
 /// The reference has no `Result` anywhere: it panics (bvh.rs:61,65-67; hittable.rs:153). Keep that behaviour.

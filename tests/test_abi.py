@@ -117,3 +117,43 @@ def test_multi_gpu_entry_points_fail_loudly_without_a_gpu(rt):
     with pytest.raises(rt.api.Rt1wError) as e:
         rt.api.Context([])
     assert e.value.status == rt.api.ERR_INVALID
+
+
+def _c_prototypes():
+    """name -> number of parameters, from include/rt1w.h."""
+    text = open(os.path.join(ROOT, "include", "rt1w.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for name, args in re.findall(r"\b(rt1w_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_shim_declares_the_whole_abi():
+    """The reference-side binding (rust/src/ffi.rs - source only, no Rust toolchain in this image) and the `extern "C"` block
+    of INTEGRATION.md stay in step with include/rt1w.h: every exported function is declared in ffi.rs with the same number
+    of parameters, every struct of the header has a #[repr(C)] mirror with the same number of fields, and INTEGRATION.md
+    names no function the header does not have."""
+    protos = _c_prototypes()
+    assert set(protos) == set(_declared_symbols())
+    rs = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    rs = re.sub(r"//[^\n]*", "", rs)
+    decl = {}
+    for name, args in re.findall(r"pub fn (rt1w_[a-z0-9_]+)\s*\(([^)]*)\)", rs, flags=re.S):
+        args = args.strip().rstrip(",")
+        decl[name] = 0 if not args else args.count(",") + 1
+    missing = sorted(set(protos) - set(decl))
+    assert not missing, f"rust/src/ffi.rs lacks {missing}"
+    assert not sorted(set(decl) - set(protos)), "rust/src/ffi.rs declares functions the header does not have"
+    wrong = {n: (protos[n], decl[n]) for n in protos if protos[n] != decl[n]}
+    assert not wrong, f"parameter counts differ (header, ffi.rs): {wrong}"
+    # structs: field counts
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rt1w.h")).read(), flags=re.S)
+    for name, body in re.findall(r"typedef struct (rt1w_[a-z0-9_]+) \{(.*?)\} \1;", hdr, flags=re.S):
+        c_fields = sum(len(decl_.split(",")) for decl_ in body.split(";") if decl_.strip())
+        m = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, flags=re.S)
+        assert m, f"rust/src/ffi.rs has no mirror of {name}"
+        assert len(re.findall(r"pub [a-z0-9_]+\s*:", m.group(1))) == c_fields, f"{name}: field count differs from the header"
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert set(re.findall(r"\b(rt1w_[a-z0-9_]+)\s*\(", doc)) - {"rt1w_main"} <= set(protos) | {"rt1w_check"}

@@ -306,6 +306,16 @@ rt1w_status rt1w_lower_prims(const rt1w_scene_desc *desc, rt1w_flat_prim *out, i
 rt1w_status rt1w_lower_face_groups(const rt1w_scene_desc *desc, int32_t *group_of_prim, int32_t *face_of_prim, int32_t capacity,
                                    int32_t *n_groups);
 
+/* Host-side only (no device needed): the two trees scene commit builds over the primitives' world-space boxes (n x 3
+ * doubles each) - the binned-SAH binary tree of 32-byte nodes (replaces `BVHNode::new`, bvh.rs:54-103: min.xyz,
+ * left_first, max.xyz, count; node 0 = root, node 1 = padding, the children of an interior node adjacent) and its
+ * SAH-optimal collapse into the compressed 8-wide tree of 80-byte nodes (layout: csrc/bvh8.h).  Every output is optional;
+ * capacities are in nodes.  prim_order[leaf] = input box of binary leaf `leaf`; wide_leaf_remap[slot primitive] = binary
+ * leaf.  Used by CPU tests of the builders (tests/test_host_bvh.py). */
+rt1w_status rt1w_build_bvh_host(const double *bbox_min3, const double *bbox_max3, int32_t n, void *nodes32, int32_t node_capacity,
+                                int32_t *n_nodes, uint32_t *prim_order, void *wide_nodes80, int32_t wide_capacity, int32_t *n_wide,
+                                uint32_t *wide_leaf_remap, int32_t *depth, int32_t *wide_depth);
+
 /* Replaces the pixel loop + ray_color (main.rs:957-1001, 51-190).
  * out_rgb_sum: HOST buffer, width*height*3 floats, row 0 = top, per-pixel SUM
  *   over the rendered sample range (not yet divided by spp).

@@ -117,7 +117,7 @@ ABI_SYMBOLS = [
     "rt1w_scene_destroy", "rt1w_scene_get_info", "rt1w_scene_get_prims", "rt1w_lower_prims", "rt1w_lower_face_groups", "rt1w_render",
     "rt1w_render_device", "rt1w_render_rgb8", "rt1w_trace_closest", "rt1w_resolve_rgb8", "rt1w_philox4x32",
     "rt1w_context_create_multi", "rt1w_comm_unique_id", "rt1w_context_comm_init", "rt1w_context_get_comm", "rt1w_shard_sample_range",
-    "rt1w_eval_light_pdf", "rt1w_eval_texture", "rt1w_eval_perlin", "rt1w_eval_dielectric", "rt1w_eval_scatter",
+    "rt1w_eval_light_pdf", "rt1w_eval_texture", "rt1w_eval_perlin", "rt1w_eval_dielectric", "rt1w_eval_scatter", "rt1w_build_bvh_host",
 ]
 
 
@@ -152,6 +152,8 @@ def load_library():
     lib.rt1w_scene_get_prims.argtypes = [vp, C.POINTER(FlatPrim), C.c_int32, C.POINTER(C.c_int32)]
     lib.rt1w_lower_prims.argtypes = [C.POINTER(SceneDesc), C.POINTER(FlatPrim), C.c_int32, C.POINTER(C.c_int32)]
     lib.rt1w_lower_face_groups.argtypes = [C.POINTER(SceneDesc), vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+    lib.rt1w_build_bvh_host.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(C.c_int32), vp, vp, C.c_int32, C.POINTER(C.c_int32), vp,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.rt1w_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     lib.rt1w_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
     lib.rt1w_trace_closest.argtypes = [vp, vp, C.c_size_t, C.c_uint64, vp, vp, vp, vp, vp]
@@ -432,6 +434,29 @@ def lower_prims(desc):
     out = (FlatPrim * max(1, n.value))()
     _check(lib.rt1w_lower_prims(dp, out, n.value, C.byref(n)))
     return list(out)[: n.value]
+
+
+# the binary tree's 32-byte node (csrc/bvh.h) and the 8-wide tree's 80-byte node (csrc/bvh8.h) as numpy records
+BVH_NODE_DTYPE = np.dtype([("min", np.float32, 3), ("left_first", np.uint32), ("max", np.float32, 3), ("count", np.uint32)])
+WIDE_NODE_DTYPE = np.dtype([("origin", np.float32, 3), ("exp", np.uint8, 3), ("imask", np.uint8), ("child_base", np.uint32),
+                            ("prim_base", np.uint32), ("leaf_mask", np.uint32), ("unused", np.uint32), ("qlo", np.uint8, (3, 8)),
+                            ("qhi", np.uint8, (3, 8))])
+
+
+def build_bvh_host(bbox_min, bbox_max):
+    """Host-side (no GPU): the SAH binary tree and its 8-wide collapse over n boxes, as scene commit builds them.
+    -> dict(nodes, prim_order, wide_nodes, wide_leaf_remap, depth, wide_depth)."""
+    lib = load_library()
+    lo, hi = np.ascontiguousarray(bbox_min, dtype=np.float64), np.ascontiguousarray(bbox_max, dtype=np.float64)
+    n = lo.shape[0]
+    n_nodes, n_wide, depth, wide_depth = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    _check(lib.rt1w_build_bvh_host(lo.ctypes.data, hi.ctypes.data, n, None, 0, C.byref(n_nodes), None, None, 0, C.byref(n_wide), None,
+                                   C.byref(depth), C.byref(wide_depth)))
+    nodes, wide = np.zeros(n_nodes.value, dtype=BVH_NODE_DTYPE), np.zeros(n_wide.value, dtype=WIDE_NODE_DTYPE)
+    order, remap = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+    _check(lib.rt1w_build_bvh_host(lo.ctypes.data, hi.ctypes.data, n, nodes.ctypes.data, n_nodes.value, C.byref(n_nodes), order.ctypes.data,
+                                   wide.ctypes.data, n_wide.value, C.byref(n_wide), remap.ctypes.data, C.byref(depth), C.byref(wide_depth)))
+    return dict(nodes=nodes, prim_order=order, wide_nodes=wide, wide_leaf_remap=remap, depth=depth.value, wide_depth=wide_depth.value)
 
 
 def lower_face_groups(desc):

@@ -398,6 +398,29 @@ rt1w_status rt1w_lower_face_groups(const rt1w_scene_desc *desc, int32_t *group_o
     return RT1W_OK;
 }
 
+rt1w_status rt1w_build_bvh_host(const double *bbox_min3, const double *bbox_max3, int32_t n, void *nodes32, int32_t node_capacity, int32_t *n_nodes,
+                                uint32_t *prim_order, void *wide_nodes80, int32_t wide_capacity, int32_t *n_wide, uint32_t *wide_leaf_remap,
+                                int32_t *depth, int32_t *wide_depth) {
+    if (!bbox_min3 || !bbox_max3 || n <= 0) return fail(RT1W_ERR_INVALID, "No objects in bvh_node constructor. (bvh.rs:61)");
+    for (size_t i = 0; i < 3 * size_t(n); ++i)
+        if (!std::isfinite(bbox_min3[i]) || !std::isfinite(bbox_max3[i]))
+            return fail(RT1W_ERR_INVALID, "No bounding box in bvh_node constructor. (bvh.rs:65-67): non-finite primitive bounds");
+    BvhBuildResult bvh;
+    build_sah_bvh(bbox_min3, bbox_max3, size_t(n), kMaxLeaf, bvh);
+    Bvh8BuildResult wide;
+    collapse_to_bvh8(bvh.nodes.data(), bvh.nodes.size(), wide);
+    if (wide.leaf_remap.size() != size_t(n)) return fail(RT1W_ERR_STATE, "wide BVH collapse lost primitives");
+    if (n_nodes) *n_nodes = int32_t(bvh.nodes.size());
+    if (n_wide) *n_wide = int32_t(wide.nodes.size());
+    if (depth) *depth = bvh.depth;
+    if (wide_depth) *wide_depth = wide.depth;
+    if (nodes32) std::memcpy(nodes32, bvh.nodes.data(), sizeof(BvhNode32) * std::min(bvh.nodes.size(), size_t(std::max(node_capacity, 0))));
+    if (wide_nodes80) std::memcpy(wide_nodes80, wide.nodes.data(), sizeof(Bvh8Node) * std::min(wide.nodes.size(), size_t(std::max(wide_capacity, 0))));
+    if (prim_order) std::memcpy(prim_order, bvh.prim_order.data(), sizeof(uint32_t) * size_t(n));
+    if (wide_leaf_remap) std::memcpy(wide_leaf_remap, wide.leaf_remap.data(), sizeof(uint32_t) * size_t(n));
+    return RT1W_OK;
+}
+
 static rt1w_status scene_create_impl(rt1w_context *ctx, const rt1w_scene_desc *desc, rt1w_scene **out) {
     *out = nullptr;
     const auto t0 = std::chrono::steady_clock::now();

@@ -229,6 +229,21 @@ extern "C" {
         capacity: i32,
         n_groups: *mut i32,
     ) -> i32;
+    pub fn rt1w_build_bvh_host(
+        bbox_min3: *const f64,
+        bbox_max3: *const f64,
+        n: i32,
+        nodes32: *mut c_void,
+        node_capacity: i32,
+        n_nodes: *mut i32,
+        prim_order: *mut u32,
+        wide_nodes80: *mut c_void,
+        wide_capacity: i32,
+        n_wide: *mut i32,
+        wide_leaf_remap: *mut u32,
+        depth: *mut i32,
+        wide_depth: *mut i32,
+    ) -> i32;
     pub fn rt1w_trace_closest(
         scene: *mut rt1w_scene,
         rays: *const rt1w_ray,

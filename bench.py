@@ -20,7 +20,7 @@ roofline  the wave kernel (scatter + closest hit + regroup, one launch per wave)
         live, against 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s
 configs   the other BASELINE.json configurations on this GPU count, each with its own roofline and (N = 1) CPU baseline:
         C2 random_scene 1200x800, C3 final_scene 800x800, C5 the 1 M-sphere stress scene 1920x1080 - timed at a reduced
-        sample count (throughput does not depend on spp), and the STRONG-scaling jobs: C4 (Cornell 3840x2160, 4096 spp in
+        sample count (128 / 128 / 64 spp per step: long enough for the ramp at the two ends of a render not to count), and the STRONG-scaling jobs: C4 (Cornell 3840x2160, 4096 spp in
         total, reduce of 99.5 MB inside the step), C1 (100 spp in total) and C5 (256 spp in total), the same job at every N
 cpu_baseline  the C++ f64 restatement of the reference (oracle/, kind "port": the Rust crate cannot be built in
         this image) on the host cores, on a bounded sample of the same workload
